@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 engine on BASELINE.json's metric:
+homomorphic ciphertext multiplies/s (BFV, N=2^14, L=8 RNS primes, t=65537, R_big =
+17 further 60-bit primes: BASELINE configs[1]) plus the forward-NTT rate at the
+same (N, L).
+
+  python bench.py --gpus N --steps K --warmup W          # our engine (one rank per GPU)
+  python bench.py --impl reference ...                   # CPU restatement of the reference path
+
+One step = one pass of tfb_bfv_mul over a batch of B independent ciphertext pairs
+already resident in HBM.  Prints ONE JSON line (rank 0)."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RING = 2 ** 14
+L_Q = 8
+L_BIG = 17
+T_PLAIN = 65537
+METRIC = "bfv_ciphertext_muls_per_s"
+UNIT = "ciphertext-muls/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(batch):
+    return (f"BFV ct*ct (rlwe_she.jl enc_mul + bfv.jl expand/contract), N=2^14, L=8x60-bit RNS primes, t=65537, "
+            f"R_big=17x60-bit primes, batch={batch} ciphertext pairs per GPU")
+
+
+def rings():
+    import toyfhe_b200 as T
+    allq, allpsi = T.prime_chain(N_RING, [60] * (L_Q + L_BIG))
+    return allq[:L_Q], allpsi[:L_Q], allq[L_Q:], allpsi[L_Q:]
+
+
+def rand_ct(rng, qs, shape):
+    import numpy as np
+    out = np.empty(shape + (len(qs), N_RING), dtype=np.uint64)
+    for i, q in enumerate(qs):
+        out[..., i, :] = rng.integers(0, q, size=shape + (N_RING,), dtype=np.uint64)
+    return out
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_bfv_mul_rate(pairs_per_step, steps, warmup):
+    """times the oracle's C restatement of the reference path on the host cores"""
+    import numpy as np
+    from oracle import c_oracle as CO
+    qs, psis, qb, psib = rings()
+    oq, ob = CO.Rns(N_RING, qs, psis), CO.Rns(N_RING, qb, psib)
+    rng = np.random.default_rng(0)
+    c1, c2 = rand_ct(rng, qs, (pairs_per_step, 2)), rand_ct(rng, qs, (pairs_per_step, 2))
+    for _ in range(warmup):
+        CO.bfv_mul(oq, ob, T_PLAIN, c1, c2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        CO.bfv_mul(oq, ob, T_PLAIN, c1, c2)
+    dt = time.perf_counter() - t0
+    return pairs_per_step * steps / dt, dt / steps, CO.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = 2
+    value, s_per_step, cores = cpu_bfv_mul_rate(pairs, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "sample": f"{pairs} ciphertext pairs per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{pairs} pairs x {args.steps} steps; C restatement of the Julia path (oracle/oracle.c), OpenMP"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import toyfhe_b200 as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    qs, psis, qb, psib = rings()
+    cq, cb = T.Context(N_RING, qs, psis, device=local), T.Context(N_RING, qb, psib, device=local)
+    rng = np.random.default_rng(1234 + rank)
+    # synthetic ciphertexts: uniform residues (what fresh ciphertext components look like, rlwe_she.jl:156-158);
+    # a 16-pair host block replicated on the device keeps host RAM small
+    blk = min(B, 16)
+    h1, h2 = rand_ct(rng, qs, (blk, 2)), rand_ct(rng, qs, (blk, 2))
+    reps = (B + blk - 1) // blk
+    c1 = cq.to_device(h1).repeat(reps, 1, 1, 1)[:B].contiguous()
+    c2 = cq.to_device(h2).repeat(reps, 1, 1, 1)[:B].contiguous()
+    # decorrelate the replicas so every pair is distinct work (values stay canonical)
+    c1 = torch.roll(c1, shifts=1, dims=3) if reps > 1 else c1
+    out = cq.empty((B, 3, L_Q, N_RING))
+    stream = torch.cuda.current_stream()
+
+    def step():
+        cq.bfv_mul(cb, T_PLAIN, c1, c2, out=out, stream=stream)
+
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    T.profile_read(reset=True)
+    T.profile_enable(True)
+    launches0 = T.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = T.kernel_launches() - launches0
+    T.profile_enable(False)
+    prof = T.profile_read(reset=True)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- standalone forward-NTT rate at (N=2^14, L=8): the other half of the metric
+    ntt_in, ntt_out = c1, torch.empty_like(c1)
+    for _ in range(3):
+        cq.ntt_fwd(ntt_in, out=ntt_out, stream=stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    KN = max(K, 10)
+    for _ in range(KN):
+        cq.ntt_fwd(ntt_in, out=ntt_out, stream=stream)
+    e1.record(stream)
+    barrier()
+    ntt_ms = e0.elapsed_time(e1) / KN
+    tn = torch.tensor([ntt_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    ntt_ms = float(tn.item())
+    ntt_polys = 2 * B
+    ntt_bytes = ntt_polys * L_Q * N_RING * 8 * 2
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    Be = min(B, 64)
+    p1 = torch.from_numpy(rand_ct(rng, qs, (Be, 2)).view(np.int64)).pin_memory()
+    p2 = torch.from_numpy(rand_ct(rng, qs, (Be, 2)).view(np.int64)).pin_memory()
+    po = torch.empty((Be, 3, L_Q, N_RING), dtype=torch.int64).pin_memory()
+    cq.bfv_mul_host(cb, T_PLAIN, p1, p2, po, stream=stream)  # warm-up (allocates staging)
+    cq.bfv_mul_host(cb, T_PLAIN, p1, p2, po, stream=stream)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        cq.bfv_mul_host(cb, T_PLAIN, p1, p2, po, stream=stream)   # synchronises before returning
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = world * Be / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    Nb = N_RING * 8
+    # algorithmic bytes per step for each kernel class of this workload
+    alg = {
+        "ntt_fwd_row": 4 * B * L_BIG * 2 * Nb,
+        "ntt_inv_row": 3 * B * L_BIG * 2 * Nb,
+        "tensor_dual": 7 * B * L_BIG * Nb,
+        "base_switch": 4 * B * (L_Q + L_BIG) * Nb,
+        "bfv_contract": 3 * B * (L_Q + L_BIG) * Nb,
+    }
+    kernels = {}
+    tot_prof_ms = sum(v[1] for v in prof.values()) or 1.0
+    for name, (cnt, ms) in prof.items():
+        if cnt == 0:
+            continue
+        kernels[name] = {"launches": cnt, "ms_total": round(ms, 4), "share": round(ms / tot_prof_ms, 4)}
+        if name in alg and ms > 0:
+            kernels[name]["achieved_gbs"] = round(alg[name] * K / (ms * 1e-3) / 1e9, 1)
+            kernels[name]["avg_launch_ms"] = round(ms / cnt, 4)
+    dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
+    roofline = None
+    if dom and "achieved_gbs" in kernels[dom]:
+        a = kernels[dom]["achieved_gbs"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
+                    "note": "61-bit modular butterflies: INT/FMA-pipe bound before HBM (see DESIGN.md)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, s_step, cores = cpu_bfv_mul_rate(2, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2 ciphertext pairs x 3 steps of the same workload; C restatement of the reference's Julia path "
+                         "(oracle/oracle.c, OpenMP over primes/coefficients) -- the Julia reference cannot run offline"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(B), "sharding": "independent ciphertext pairs per GPU, no data-path collective",
+                   "l2": f"inputs {2 * B * 2 * L_Q * Nb / 2**20:.0f} MiB + R_big intermediates per step, far larger than the 126 MB L2 (no flush needed)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * 2 * L_Q * Nb),
+                "d2h_bytes_per_step": int(Be * 3 * L_Q * Nb), "batch": Be, "ms_per_step": e2e_s * 1e3,
+                "api": "tfb_bfv_mul_host (pinned host buffers, H2D + compute + D2H per step)"},
+        "roofline": roofline,
+        "kernels": kernels,
+        "ntt_fwd": {"value": world * ntt_polys / (ntt_ms * 1e-3), "unit": "RNS-NTT/s (N=2^14, L=8)",
+                    "prime_rows_per_s": world * ntt_polys * L_Q / (ntt_ms * 1e-3), "ms_per_step": ntt_ms,
+                    "achieved_gbs": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "frac_of_peak": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / peak,
+                    "algorithmic_bytes_per_launch": ntt_bytes},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

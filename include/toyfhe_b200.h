@@ -1,0 +1,160 @@
+/* toyfhe_b200.h -- C-ABI of libtoyfhe_b200.so, the B200 (sm_100a) engine behind
+ * ToyFHE.jl's power-of-two cyclotomic ring path.
+ *
+ * The reference has no FFI today: the seam is Julia multiple dispatch on the
+ * RingElement storage type.  Each entry point below names the reference method
+ * it replaces (paths relative to the ToyFHE.jl repository); INTEGRATION.md shows
+ * the `ccall` stubs a maintainer would add at exactly those methods.
+ *
+ * Conventions
+ *   - element  = one residue in one 64-bit word, canonical in [0,q)  (PrimeField.n)
+ *   - RNS poly = u64 [L][N], residue-major (StructArray fieldarrays, crt.jl:150-156)
+ *   - batches  = u64 [batch][components][L][N]; "rows" counts [N]-rows, row r
+ *                belongs to prime r % L (rows must be a multiple of L)
+ *   - all buffer arguments are DEVICE pointers, except in the *_host entry points,
+ *     which take HOST pointers and do the host<->device copies themselves
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous on that stream; calls on one ctx must be serialised by the caller
+ *   - in-place (out == in) is allowed unless stated otherwise
+ *   - every function returns 0 on success or a TFB_E* code; the message is
+ *     available from tfb_last_error() (thread-local).  Nothing throws or aborts
+ *     across the ABI (the reference raises Julia exceptions / @assert:
+ *     pow2_cyc_rings.jl:31,61,116; rlwe_she.jl:223-225,248; crt.jl:269-275).
+ *   - moduli must be odd primes < 2^62 with q = 1 (mod 2N); psi a primitive 2N-th
+ *     root (pow2_cyc_rings.jl:27-47).
+ */
+#ifndef TOYFHE_B200_H
+#define TOYFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfb_ctx tfb_ctx;
+
+enum {
+    TFB_OK = 0,
+    TFB_EINVAL = 1,       /* invalid argument (UsageError / @assert in the reference) */
+    TFB_ECUDA = 2,        /* CUDA runtime failure */
+    TFB_EUNSUPPORTED = 3, /* e.g. N > 2^16, modulus >= 2^62 */
+    TFB_ENOMEM = 4
+};
+
+/* ---- diagnostics -------------------------------------------------------- */
+const char* tfb_last_error(void);
+int tfb_version(void);
+/* number of engine kernels launched by this process so far (bench.py "gpu_launches") */
+unsigned long long tfb_kernel_launches(void);
+
+/* per-kernel-class device timing (CUDA events on the launching stream), used by
+ * bench.py for the roofline figures: enable, run, then read totals per class. */
+int tfb_profile_enable(int on);
+int tfb_profile_classes(void);
+const char* tfb_profile_class_name(int cls);
+int tfb_profile_read(unsigned long long* counts, double* total_ms, int reset);
+
+/* ---- ring construction helpers (host only, no GPU needed) ---------------- */
+/* NegacyclicRing(N, logqs) prime chain, crt.jl:282-295: ascending-logq order,
+ * p = nextprime(max(2^logq+1, last+2N); interval=2N); psi = minimal primitive
+ * 2N-th root of each prime (GaloisFields.minimal_primitive_root, crt.jl:142-144). */
+int tfb_prime_chain(uint32_t N, const int32_t* logqs, uint32_t n, uint64_t* q_out, uint64_t* psi_out);
+/* GaloisFields.minimal_primitive_root(F_q, n), n a power of two (pow2_cyc_rings.jl:40) */
+int tfb_minimal_primitive_root(uint64_t q, uint64_t n, uint64_t* out);
+/* ndigits(Q, base=2^w) for Q = prod q_i (rlwe_she.jl:280,333) */
+int tfb_ndigits(const uint64_t* q, uint32_t L, uint32_t w, uint32_t* out);
+
+/* ---- context = one NegacyclicRing{CRTEncoded{L}, N}(psi) ------------------ */
+/* pow2_cyc_rings.jl:27-47 + crt.jl:282-295.  Precomputes twiddle / Garner tables
+ * on `device` (the reference rebuilds twiddles on every transform, :298-301). */
+int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const uint64_t* psi, tfb_ctx** out);
+int tfb_ctx_destroy(tfb_ctx* ctx);
+int tfb_ctx_info(const tfb_ctx* ctx, uint32_t* N, uint32_t* L, uint64_t* q /*[L] or NULL*/, uint64_t* psi /*[L] or NULL*/);
+
+/* ---- device memory helpers for hosts without their own CUDA binding ------- */
+int tfb_malloc(tfb_ctx* ctx, size_t bytes, void** dptr);
+int tfb_free(tfb_ctx* ctx, void* dptr);
+int tfb_memcpy_h2d(tfb_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int tfb_memcpy_d2h(tfb_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int tfb_sync(tfb_ctx* ctx, void* stream);
+
+/* ---- transforms ----------------------------------------------------------- */
+/* NTT.nntt: c^[k] = sum_j c[j] psi^(j(2k+1)), natural order in and out
+ * (pow2_cyc_rings.jl:295-303; RNS dispatch crt.jl:247-256). */
+int tfb_ntt_fwd(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream);
+/* NTT.inntt (pow2_cyc_rings.jl:308-318; crt.jl:258-267). */
+int tfb_ntt_inv(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream);
+
+/* ---- coefficient-wise ring ops (either domain) ----------------------------- */
+/* CRTEncoded + - * (crt.jl:120-134) broadcast over RingElement storage
+ * (pow2_cyc_rings.jl:167, 192-219) */
+int tfb_add(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);
+int tfb_sub(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);
+int tfb_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);
+int tfb_neg(tfb_ctx* ctx, const uint64_t* a, uint64_t* out, uint64_t rows, void* stream);
+/* scalar_mul (pow2_cyc_rings.jl:177-185); s_residues = HOST array [L], s mod q_i */
+int tfb_scalar_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* s_residues, uint64_t* out, uint64_t rows, void* stream);
+
+/* ring_multiply / * (pow2_cyc_rings.jl:147-173): primal in, primal out */
+int tfb_ring_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);
+
+/* apply_galois_element on primal rows (pow2_cyc_rings.jl:321-329); g odd; not in place */
+int tfb_galois(tfb_ctx* ctx, uint64_t g, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream);
+
+/* ---- RNS level changes ------------------------------------------------------ */
+/* modswitch(::RingElement) = exact division by the last prime, CKKS rescale
+ * (crt.jl:215-220, 226-228; ckksencoding.jl:127-130): in [polys][L][N] -> out [polys][L-1][N] */
+int tfb_rescale(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+/* c .* CRTExpand{P}: multiply by P, append a zero residue (crt.jl:35-40;
+ * modulusraising.jl:35-41): in [polys][L][N] -> out [polys][L+1][N] */
+int tfb_crt_expand(tfb_ctx* ctx, uint64_t P, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+
+/* ---- ciphertext multiply ----------------------------------------------------- */
+/* enc_mul without basis change (CKKS / BGV form, rlwe_she.jl:247-262 with the
+ * default mul_expand/mul_contract): c1,c2 [batch][2][L][N] primal -> out [batch][3][L][N] primal */
+int tfb_ct_tensor(tfb_ctx* ctx, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
+
+/* BFV mul_expand = switch(R_big, c) (bfv.jl:34, 202-226): centred lift from
+ * ctx_from's modulus, reduced into ctx_to's basis: in [polys][Lf][N] -> out [polys][Lt][N] */
+int tfb_bfv_switch(tfb_ctx* ctx_from, tfb_ctx* ctx_to, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+/* BFV mul_contract = switch(R, multround(e, t, Q)) (bfv.jl:35-40, 172-190, rounding
+ * div_hacks.jl:120-135): in [polys][Lb][N] over ctx_big -> out [polys][L][N] over ctx_q */
+int tfb_bfv_contract(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+/* BFV ciphertext multiply = expand, tensor in R_big, contract
+ * (rlwe_she.jl:247-262 with bfv.jl:34-40): c1,c2 [batch][2][L][N] -> out [batch][3][L][N] */
+int tfb_bfv_mul(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
+
+/* ---- key switching ------------------------------------------------------------ */
+/* Digit polynomials of keyswitch (rlwe_she.jl:326-338).  cend = last ciphertext
+ * component [batch][L][N] (primal, contiguous); relin_window w == 0 -> CRT digits
+ * (D = L, centred residue re-embedded), w > 0 -> base-2^w digits of the un-centred
+ * integer (D = ndigits(Q, 2^w)).  Digits are embedded in ctx_target's basis
+ * (ctx itself, or the raised ring): out [batch][D][Lt][N] primal. */
+int tfb_keyswitch_digits(tfb_ctx* ctx, tfb_ctx* ctx_target, uint32_t w, const uint64_t* cend, uint64_t* out, uint64_t batch, void* stream);
+/* keyswitch(ek, c) (rlwe_she.jl:315-347).  key_dual = evaluation key already in
+ * the NTT domain (the reference caches key.mask/key.masked duals in the
+ * RingElement), [D][2][L'][N] with component 0 = mask, 1 = masked, over ctx's
+ * primes (L' = L) or, when ctx_ext != NULL (ModulusRaised, modulusraising.jl:35-49),
+ * over ctx_ext's primes = ctx's primes followed by the special prime (L' = L+1);
+ * the host picks those key rows (downswitch_keyelement, crt.jl:238-244,
+ * modulusraising.jl:43-49).  ct [batch][comps][L][N] primal, comps in {2,3};
+ * out [batch][2][L][N] primal. */
+int tfb_keyswitch(tfb_ctx* ctx, tfb_ctx* ctx_ext, uint32_t w, const uint64_t* key_dual, uint32_t D,
+                  const uint64_t* ct, uint32_t comps, uint64_t* out, uint64_t batch, void* stream);
+
+/* ---- host-buffer entry points (pinned or pageable host memory) ------------------ */
+/* Same semantics as the device versions; copies in, runs, copies out and
+ * synchronises `stream` before returning. */
+int tfb_ntt_fwd_host(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream);
+int tfb_ntt_inv_host(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream);
+int tfb_ring_mul_host(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);
+int tfb_ct_tensor_host(tfb_ctx* ctx, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
+int tfb_bfv_mul_host(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
+int tfb_rescale_host(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOYFHE_B200_H */

@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on
+the same seeded inputs -- bit-exact (all arithmetic is integer).  Run with
+``pytest -m gpu`` on a B200."""
+import math
+
+import numpy as np
+import pytest
+
+import toyfhe_b200 as T
+from oracle import c_oracle as CO
+from oracle import toyfhe_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, N, qs, shape=()):
+    out = np.empty(shape + (len(qs), N), dtype=np.uint64)
+    for i, q in enumerate(qs):
+        out[..., i, :] = rng.integers(0, q, size=shape + (N,), dtype=np.uint64)
+    return out
+
+
+def _ring(N, logqs):
+    qs, psis = T.prime_chain(N, logqs)
+    return qs, psis, T.Context(N, qs, psis), CO.Rns(N, qs, psis)
+
+
+H = T.Context.to_host
+
+
+# ---------------------------------------------------------------- doc KATs on the GPU
+def test_doc_kats_on_gpu():
+    # docs/src/man/background/rlwe.md:183-212 : Z_97[x]/(x^4+1), psi = 33
+    ctx = T.Context(4, [97], [33])
+    d = lambda v: ctx.to_device(np.array([v], dtype=np.uint64))
+    p1, p2, p3, p4 = d([1, 1, 0, 0]), d([0, 0, 0, 1]), d([4, 0, 0, 0]), d([5, 0, 0, 0])
+    assert H(ctx.ring_mul(p3, p4)).tolist() == [[20, 0, 0, 0]]
+    assert H(ctx.ring_mul(p1, p1)).tolist() == [[1, 2, 1, 0]]
+    assert H(ctx.ring_mul(p1, p2)).tolist() == [[96, 0, 0, 1]]
+    assert H(ctx.ntt_fwd(p1)).tolist() == [[34, 48, 65, 51]]
+    assert H(ctx.galois(d([1, 2, 3, 4]), 3)).tolist() == [[1, 4, 94, 2]]
+    # docs/src/man/encoding.md:69-92 : slot product at p = 65537, N = 2048
+    N, q = 2048, 65537
+    psi = T.minimal_primitive_root(q, 2 * N)
+    c = T.Context(N, [q], [psi])
+    a_slots = np.zeros((1, N), dtype=np.uint64); a_slots[0, :10] = np.arange(1, 11)
+    b_slots = np.full((1, N), 10, dtype=np.uint64)
+    a = c.ntt_inv(c.to_device(a_slots)); b = c.ntt_inv(c.to_device(b_slots))
+    prod = c.ntt_fwd(c.ring_mul(a, b))
+    assert H(prod)[0, :11].tolist() == [10, 20, 30, 40, 50, 60, 70, 80, 90, 100, 0]
+    # src/cryptparams.jl:22-25 PALISADE rings: product against the naive O(N^2) definition
+    for (q, N, psi) in [(1099511627873, 8, 108163207722), (525313, 512, 513496)]:
+        c = T.Context(N, [q], [psi])
+        rng = np.random.default_rng(N)
+        x = rng.integers(0, q, size=(1, N), dtype=np.uint64); y = rng.integers(0, q, size=(1, N), dtype=np.uint64)
+        want = O.ring_multiply_naive([int(v) for v in x[0]], [int(v) for v in y[0]], q)
+        assert [int(v) for v in H(c.ring_mul(c.to_device(x), c.to_device(y)))[0]] == want
+
+
+# ---------------------------------------------------------------------- transforms
+@pytest.mark.parametrize("logN", [1, 2, 4, 5, 9, 10, 11, 12, 13, 14, 15, 16])
+def test_ntt_parity_all_sizes(logN):
+    N = 1 << logN
+    qs, psis, ctx, orc = _ring(N, [60, 40, 60] if logN >= 4 else [40, 50, 60])
+    rng = np.random.default_rng(logN)
+    B = 3 if logN >= 15 else 5
+    a = _rand(rng, N, qs, (B,))
+    # edge rows: zeros, all q-1, single one
+    a[0, 0, :] = 0
+    a[0, 1, :] = qs[1] - 1
+    a[0, 2, :] = 0; a[0, 2, N - 1] = 1
+    d = ctx.to_device(a)
+    f = ctx.ntt_fwd(d)
+    want = orc.nntt(a)
+    assert np.array_equal(H(f), want)
+    assert np.array_equal(H(ctx.ntt_inv(f)), a)
+    assert np.array_equal(H(ctx.ntt_inv(ctx.to_device(a))), orc.inntt(a))
+    # in place
+    d2 = d.clone()
+    ctx.ntt_fwd(d2, out=d2)
+    assert np.array_equal(H(d2), want)
+    ctx.ntt_inv(d2, out=d2)
+    assert np.array_equal(H(d2), a)
+
+
+def test_ntt_headline_config_full_batch(q8, psi8):
+    """N = 2^14, L = 8 (BASELINE configs[1]): parity on two polys against the oracle,
+    then size-independent properties on a batch larger than L2."""
+    N = 2 ** 14
+    ctx, orc = T.Context(N, q8, psi8), CO.Rns(N, q8, psi8)
+    rng = np.random.default_rng(14)
+    a = _rand(rng, N, q8, (2,))
+    assert np.array_equal(H(ctx.ntt_fwd(ctx.to_device(a))), orc.nntt(a))
+    B = 160  # 160 MiB of residues
+    big = ctx.to_device(_rand(rng, N, q8, (B,)))
+    f = ctx.ntt_fwd(big)
+    assert bool((ctx.ntt_inv(f) == big).all())
+    # linearity: NTT(x + y) = NTT(x) + NTT(y)
+    y = ctx.to_device(_rand(rng, N, q8, (B,)))
+    lhs = ctx.ntt_fwd(ctx.add(big, y))
+    rhs = ctx.add(f, ctx.ntt_fwd(y))
+    assert bool((lhs == rhs).all())
+    # every output canonical
+    qcol = ctx.to_device(np.array(q8, dtype=np.uint64)).view(1, 8, 1)
+    assert bool(((f >= 0) & (f < qcol)).all())  # int64 view is fine: q < 2^62
+
+
+def test_elementwise_and_ring_ops():
+    N = 1024
+    qs, psis, ctx, orc = _ring(N, [60, 45, 40, 60])
+    rng = np.random.default_rng(2)
+    a, b = _rand(rng, N, qs, (3,)), _rand(rng, N, qs, (3,))
+    a[0, :, :4] = 0
+    b[0, :, :4] = 0
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    assert np.array_equal(H(ctx.add(da, db)), orc.add(a, b))
+    assert np.array_equal(H(ctx.sub(da, db)), orc.sub(a, b))
+    assert np.array_equal(H(ctx.mul(da, db)), orc.mul(a, b))
+    assert np.array_equal(H(ctx.neg(da)), orc.neg(a))
+    s = 123456789012345678901234567890
+    assert np.array_equal(H(ctx.scalar_mul(da, s)), orc.scalar_mul(a, s))
+    assert np.array_equal(H(ctx.ring_mul(da, db)), orc.ring_mul(a, b))
+    for g in (3, 5, 2 * N - 1, pow(3, 2 * N - 1, 2 * N)):
+        assert np.array_equal(H(ctx.galois(da, g)), orc.galois(a, g))
+    assert np.array_equal(H(ctx.rescale(da)), orc.modswitch(a))
+    qs3, psis3 = qs[:3], psis[:3]
+    c3, o3 = T.Context(N, qs3, psis3), CO.Rns(N, qs3, psis3)
+    a3 = np.ascontiguousarray(a[:, :3, :])
+    assert np.array_equal(H(c3.crt_expand(c3.to_device(a3), qs[3])), o3.crt_expand(a3, qs[3]))
+
+
+def test_small_ring_ops_like_reference_ckks_tests():
+    # test/ckks_modswitch.jl: N = 32, three 40-bit primes
+    N = 32
+    qs, psis, ctx, orc = _ring(N, [40, 40, 40])
+    rng = np.random.default_rng(3)
+    a, b = _rand(rng, N, qs, (2,)), _rand(rng, N, qs, (2,))
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    assert np.array_equal(H(ctx.ring_mul(da, db)), orc.ring_mul(a, b))
+    assert np.array_equal(H(ctx.rescale(da)), orc.modswitch(a))
+    assert np.array_equal(H(ctx.galois(da, 3)), orc.galois(a, 3))
+
+
+# ------------------------------------------------------------- ciphertext multiply
+@pytest.mark.parametrize("N,logqs,B", [(32, [40, 40, 40], 2), (2048, [50, 50], 2), (2 ** 14, [60] * 8, 2)])
+def test_ct_tensor(N, logqs, B):
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(N)
+    c1, c2 = _rand(rng, N, qs, (B, 2)), _rand(rng, N, qs, (B, 2))
+    got = H(ctx.ct_tensor(ctx.to_device(c1), ctx.to_device(c2)))
+    assert np.array_equal(got, orc.ct_tensor(c1, c2))
+
+
+@pytest.mark.parametrize("N,L,Lb,t,B", [(32, 2, 4, 53, 2), (2048, 2, 4, 53, 1), (1024, 8, 17, 65537, 1)])
+def test_bfv_switch_contract_mul(N, L, Lb, t, B):
+    allq, allpsi = T.prime_chain(N, [60 if L == 8 else 50] * (L + Lb))
+    qs, psis, qb, psib = allq[:L], allpsi[:L], allq[L:], allpsi[L:]
+    cq, cb = T.Context(N, qs, psis), T.Context(N, qb, psib)
+    oq, ob = CO.Rns(N, qs, psis), CO.Rns(N, qb, psib)
+    rng = np.random.default_rng(N + L)
+    c1, c2 = _rand(rng, N, qs, (B, 2)), _rand(rng, N, qs, (B, 2))
+    Q, Qb = math.prod(qs), math.prod(qb)
+    for k, X in enumerate([Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]):   # strict '>' rule, bfv.jl:202-220
+        for i, q in enumerate(qs):
+            c1[0, 0, i, k] = X % q
+    e1 = H(cq.bfv_switch(cb, cq.to_device(c1)))
+    assert np.array_equal(e1, CO.bfv_switch(N, qs, qb, c1))
+    big = _rand(rng, N, qb, (3,))
+    for k, X in enumerate([Qb >> 1, (Qb >> 1) + 1, 0, 1, Qb - 1, Q >> 1, (Q >> 1) + 1, Q, Q - 1]):
+        for j, p in enumerate(qb):
+            big[0, j, k] = X % p
+    got = H(cq.bfv_contract(cb, t, cb.to_device(big)))
+    assert np.array_equal(got, CO.bfv_contract(N, qs, qb, t, big))
+    gm = H(cq.bfv_mul(cb, t, cq.to_device(c1), cq.to_device(c2)))
+    assert np.array_equal(gm, CO.bfv_mul(oq, ob, t, c1, c2))
+
+
+def test_bfv_mul_headline_config(q8, psi8):
+    """BASELINE configs[1]: N = 2^14, L = 8, t = 65537, R_big = 17 further primes."""
+    N = 2 ** 14
+    allq, allpsi = T.prime_chain(N, [60] * 25)
+    assert allq[:8] == q8
+    qb, psib = allq[8:], allpsi[8:]
+    cq, cb = T.Context(N, q8, psi8), T.Context(N, qb, psib)
+    oq, ob = CO.Rns(N, q8, psi8), CO.Rns(N, qb, psib)
+    rng = np.random.default_rng(99)
+    c1, c2 = _rand(rng, N, q8, (1, 2)), _rand(rng, N, q8, (1, 2))
+    gm = H(cq.bfv_mul(cb, 65537, cq.to_device(c1), cq.to_device(c2)))
+    assert np.array_equal(gm, CO.bfv_mul(oq, ob, 65537, c1, c2))
+
+
+# --------------------------------------------------------------------- key switching
+@pytest.mark.parametrize("w", [0, 1, 2, 7, 31])
+def test_keyswitch_digits(w):
+    N = 64
+    qs, psis, ctx, orc = _ring(N, [60, 60, 40])
+    rng = np.random.default_rng(w)
+    cend = _rand(rng, N, qs, (2,))
+    got = H(ctx.keyswitch_digits(ctx.to_device(cend), w))
+    for b in range(2):
+        assert np.array_equal(got[b], orc.keyswitch_digits(cend[b], w))
+
+
+@pytest.mark.parametrize("N,logqs,w,comps", [(64, [60, 60, 40], 0, 3), (64, [60, 60, 40], 7, 3), (64, [50, 50], 1, 2),
+                                             (2048, [50, 50], 1, 3), (1024, [60] * 4, 2, 3)])
+def test_keyswitch_plain(N, logqs, w, comps):
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(N + w)
+    D = ctx.L if w == 0 else T.ndigits(qs, w)
+    key = _rand(rng, N, qs, (D, 2))
+    B = 2
+    ct = _rand(rng, N, qs, (B, comps))
+    key_dual = ctx.ntt_fwd(ctx.to_device(key))
+    got = H(ctx.keyswitch(key_dual, ctx.to_device(ct), w))
+    for b in range(B):
+        dg = orc.keyswitch_digits(ct[b, comps - 1], w)
+        c1 = ct[b, 0]
+        c2 = ct[b, 1] if comps == 3 else np.zeros_like(ct[b, 0])
+        w1, w2 = orc.keyswitch_accum(dg, key, c1, c2)
+        assert np.array_equal(got[b, 0], w1) and np.array_equal(got[b, 1], w2)
+
+
+def test_keyswitch_modulus_raised_matches_python_oracle():
+    # test/ckks_modraise.jl shape: N = 32, (q0, q1, special), CRT digits
+    N = 32
+    qs, psis = T.prime_chain(N, [40, 40, 40])
+    ctx_ct = T.Context(N, qs[:2], psis[:2])
+    ctx_ext = T.Context(N, qs, psis)
+    rng = np.random.default_rng(5)
+    key = _rand(rng, N, qs, (3, 2))           # one component per prime of the key ring (incl. special)
+    ct = _rand(rng, N, qs[:2], (2, 2))
+    key_dual = ctx_ext.ntt_fwd(ctx_ext.to_device(key[:2]))   # digits 0..1, rows [q0, q1, special]
+    got = H(ctx_ct.keyswitch(key_dual, ctx_ct.to_device(ct), 0, ext=ctx_ext))
+    tl = lambda a: [[int(x) for x in r] for r in a]
+    for b in range(2):
+        want = O.keyswitch_modraised([tl(ct[b, 0]), tl(ct[b, 1])], [(tl(key[d, 0]), tl(key[d, 1])) for d in range(3)], qs, psis, 0)
+        assert tl(got[b, 0]) == want[0] and tl(got[b, 1]) == want[1]
+
+
+# ----------------------------------------------------------------- host entry points
+def test_host_entry_points(q8, psi8):
+    import torch
+    N = 4096
+    qs, psis, ctx, orc = _ring(N, [60, 60, 60])
+    rng = np.random.default_rng(8)
+    a, b = _rand(rng, N, qs, (2,)), _rand(rng, N, qs, (2,))
+    out = np.empty_like(a)
+    ctx.ntt_fwd_host(a, out)
+    assert np.array_equal(out, orc.nntt(a))
+    ctx.ntt_inv_host(out, out)
+    assert np.array_equal(out, a)
+    ctx.ring_mul_host(a, b, out)
+    assert np.array_equal(out, orc.ring_mul(a, b))
+    c1, c2 = _rand(rng, N, qs, (2, 2)), _rand(rng, N, qs, (2, 2))
+    pin = lambda x: torch.from_numpy(x.view(np.int64)).pin_memory()
+    o3 = torch.empty((2, 3, 3, N), dtype=torch.int64).pin_memory()
+    ctx.ct_tensor_host(pin(c1), pin(c2), o3)
+    assert np.array_equal(o3.numpy().view(np.uint64), orc.ct_tensor(c1, c2))
+    r = np.empty((2, 2, N), dtype=np.uint64)
+    ctx.rescale_host(a, r)
+    assert np.array_equal(r, orc.modswitch(a))
+
+
+def test_error_paths():
+    N = 1024
+    qs, psis, ctx, _ = _ring(N, [60, 60])
+    x = ctx.empty((3, N))  # not a multiple of L rows
+    with pytest.raises(AssertionError):
+        ctx.ntt_fwd(x)
+    import ctypes as C
+    lib = T.load_library()
+    rc = lib.tfb_ntt_fwd(ctx.h, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), C.c_uint64(3), None)
+    assert rc == 1 and b"multiple" in lib.tfb_last_error()
+    rc = lib.tfb_ntt_fwd(ctx.h, None, None, C.c_uint64(0), None)   # empty input is fine
+    assert rc == 0
+    with pytest.raises(T.EngineError):
+        ctx.galois(ctx.empty((2, N)), 4)                           # even Galois element
+    with pytest.raises(T.EngineError):
+        T.Context(1 << 17, [97], [33])

@@ -1,0 +1,598 @@
+// C-ABI of libtoyfhe_b200.so (see include/toyfhe_b200.h for the contract and the
+// reference methods each entry point replaces).
+#include <cstring>
+
+#include "engine.h"
+#include "tables.h"
+
+static thread_local std::string g_err;
+void tfb_set_error(const std::string& msg) { g_err = msg; }
+int tfb_cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return TFB_ECUDA;
+}
+
+#define CHECK_CTX(c)                                                  \
+    do {                                                              \
+        if (!(c)) { tfb_set_error("null context"); return TFB_EINVAL; } \
+    } while (0)
+#define CHECK_ROWS(c, rows)                                                                         \
+    do {                                                                                            \
+        if ((rows) % (c)->L) { tfb_set_error("rows must be a multiple of the number of primes"); return TFB_EINVAL; } \
+    } while (0)
+#define CHECK_PTR(p)                                                       \
+    do {                                                                   \
+        if (!(p)) { tfb_set_error("null buffer: " #p); return TFB_EINVAL; } \
+    } while (0)
+
+static int grow(void** p, size_t* have, size_t bytes) {
+    if (*have >= bytes) return TFB_OK;
+    if (*p) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return tfb_cuda_fail(e, "cudaDeviceSynchronize");
+        cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        tfb_set_error("out of device memory for engine scratch");
+        return TFB_ENOMEM;
+    }
+    *have = want;
+    return TFB_OK;
+}
+int ws_reserve(tfb_ctx* c, size_t bytes) { return grow(&c->ws, &c->ws_bytes, bytes); }
+int stage_reserve(tfb_ctx* c, size_t bytes) { return grow(&c->stage, &c->stage_bytes, bytes); }
+
+// ------------------------------------------------------------------ profiling
+#include <mutex>
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static unsigned long long g_prof_count[PC_COUNT];
+static double g_prof_ms[PC_COUNT];
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), stop(nullptr) {
+    tfb_count_launch();
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t a = prof_event();
+    stop = prof_event();
+    cudaEventRecord(a, st);
+    g_prof_recs.push_back({cls, a, stop});
+}
+ProfScope::~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+}
+static const char* kProfNames[PC_COUNT] = {"ntt_fwd_row", "ntt_inv_row", "ntt_other", "elementwise", "tensor_dual",
+                                           "base_switch", "bfv_contract", "ks_digits", "ks_accum", "ks_finish", "level"};
+
+extern "C" {
+
+int tfb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return TFB_OK;
+}
+// drains the recorded launches (synchronises their events) into per-class totals;
+// counts/ms are arrays of tfb_profile_classes() entries and are ADDED to.
+int tfb_profile_read(unsigned long long* counts, double* ms, int reset) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) return tfb_cuda_fail(e, "cudaEventSynchronize");
+        float t = 0;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        g_prof_count[r.cls]++;
+        g_prof_ms[r.cls] += t;
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    for (int i = 0; i < PC_COUNT; i++) {
+        if (counts) counts[i] = g_prof_count[i];
+        if (ms) ms[i] = g_prof_ms[i];
+        if (reset) { g_prof_count[i] = 0; g_prof_ms[i] = 0; }
+    }
+    return TFB_OK;
+}
+int tfb_profile_classes(void) { return PC_COUNT; }
+const char* tfb_profile_class_name(int i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }
+
+const char* tfb_last_error(void) { return g_err.c_str(); }
+int tfb_version(void) { return 100; }
+unsigned long long tfb_kernel_launches(void) { return tfb_launch_count(); }
+
+int tfb_minimal_primitive_root(uint64_t q, uint64_t n, uint64_t* out) {
+    if (!out || !h_is_prime(q) || !h_minimal_primitive_root(q, n, out)) {
+        tfb_set_error("no primitive n-th root: need prime q with n | q-1, n a power of two");
+        return TFB_EINVAL;
+    }
+    return TFB_OK;
+}
+
+int tfb_prime_chain(uint32_t N, const int32_t* logqs, uint32_t n, uint64_t* q_out, uint64_t* psi_out) {
+    if (!logqs || !q_out || !N || (N & (N - 1))) { tfb_set_error("prime chain: bad arguments"); return TFB_EINVAL; }
+    // ascending-logq generation order (stable), results in the caller's order (crt.jl:283-291)
+    std::vector<uint32_t> perm(n);
+    for (uint32_t i = 0; i < n; i++) perm[i] = i;
+    for (uint32_t i = 1; i < n; i++)
+        for (uint32_t j = i; j > 0 && logqs[perm[j - 1]] > logqs[perm[j]]; j--) std::swap(perm[j - 1], perm[j]);
+    u64 last = 0;
+    const u64 step = 2ull * N;
+    for (uint32_t k = 0; k < n; k++) {
+        const int lq = logqs[perm[k]];
+        if (lq < 2 || lq > 61) { tfb_set_error("prime chain: logq must be in 2..61"); return TFB_EUNSUPPORTED; }
+        u64 p = (1ull << lq) + 1;
+        if (last + step > p) p = last + step;
+        while (!h_is_prime(p)) {
+            p += step;
+            if (p >> 62) { tfb_set_error("prime chain: ran past 2^62"); return TFB_EUNSUPPORTED; }
+        }
+        last = p;
+        q_out[perm[k]] = p;
+    }
+    if (psi_out)
+        for (uint32_t i = 0; i < n; i++)
+            if (!h_minimal_primitive_root(q_out[i], step, &psi_out[i])) { tfb_set_error("prime chain: no 2N-th root"); return TFB_EINVAL; }
+    return TFB_OK;
+}
+
+int tfb_ndigits(const uint64_t* q, uint32_t L, uint32_t w, uint32_t* out) {
+    if (!q || !out || !L || !w) { tfb_set_error("ndigits: bad arguments"); return TFB_EINVAL; }
+    // bit length of Q = prod q_i with a little-endian limb product
+    std::vector<u64> X(1, 1);
+    for (uint32_t i = 0; i < L; i++) {
+        u64 carry = 0;
+        for (size_t k = 0; k < X.size(); k++) {
+            u128 t = (u128)X[k] * q[i] + carry;
+            X[k] = (u64)t;
+            carry = (u64)(t >> 64);
+        }
+        if (carry) X.push_back(carry);
+    }
+    size_t bits = (X.size() - 1) * 64 + (64 - __builtin_clzll(X.back()));
+    *out = (uint32_t)((bits + w - 1) / w);
+    return TFB_OK;
+}
+
+int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const uint64_t* psi, tfb_ctx** out) {
+    if (!out || !q || !psi) { tfb_set_error("ctx_create: null argument"); return TFB_EINVAL; }
+    *out = nullptr;
+    if (N < 2 || (N & (N - 1))) { tfb_set_error("ctx_create: N must be a power of two >= 2"); return TFB_EINVAL; }
+    if (N > (1u << 16)) { tfb_set_error("ctx_create: N > 2^16 is not supported"); return TFB_EUNSUPPORTED; }
+    if (L < 1 || L > TFB_MAX_L) { tfb_set_error("ctx_create: L must be in 1..64"); return TFB_EINVAL; }
+    for (uint32_t i = 0; i < L; i++) {
+        if (q[i] >> 62) { tfb_set_error("ctx_create: modulus must be < 2^62"); return TFB_EUNSUPPORTED; }
+        if (q[i] < 3 || (q[i] - 1) % (2ull * N)) { tfb_set_error("ctx_create: need q = 1 (mod 2N)"); return TFB_EINVAL; }
+        if (!h_is_prime(q[i])) { tfb_set_error("ctx_create: modulus is not prime"); return TFB_EINVAL; }
+        if (psi[i] >= q[i]) { tfb_set_error("ctx_create: psi must be < q"); return TFB_EINVAL; }
+        // is_primitive_root(psi, 2N) (pow2_cyc_rings.jl:22,31) -- we also require psi^N = -1
+        if (h_powmod(psi[i], N, q[i]) != q[i] - 1) { tfb_set_error("ctx_create: psi is not a primitive 2N-th root of unity"); return TFB_EINVAL; }
+        for (uint32_t j = 0; j < i; j++)
+            if (q[j] == q[i]) { tfb_set_error("ctx_create: repeated modulus"); return TFB_EINVAL; }
+    }
+    TFB_CUDA(cudaSetDevice(device));
+    tfb_ctx* c = new tfb_ctx();
+    c->device = device;
+    c->N = N;
+    c->L = L;
+    c->logN = 0;
+    while ((1u << c->logN) < N) c->logN++;
+    c->q.assign(q, q + L);
+    c->psi.assign(psi, psi + L);
+    c->d_fwd = c->d_inv = nullptr;
+    c->d_pp = nullptr;
+    c->d_ginv = nullptr;
+    c->d_halfmr = nullptr;
+    c->ws = c->stage = c->io = nullptr;
+    c->ws_bytes = c->stage_bytes = c->io_bytes = 0;
+    c->conv_ok = false;
+    std::vector<tw_t> fwd((size_t)L * N), inv((size_t)L * N);
+    std::vector<PrimeParams> pp(L);
+    for (uint32_t i = 0; i < L; i++) {
+        HostTables ht;
+        build_tables(N, q[i], psi[i], ht);
+        memcpy(&fwd[(size_t)i * N], ht.fwd.data(), (size_t)N * sizeof(tw_t));
+        memcpy(&inv[(size_t)i * N], ht.inv.data(), (size_t)N * sizeof(tw_t));
+        pp[i].pc = ht.pc;
+        pp[i].ninv = ht.ninv;
+        pp[i].ninv_w1 = ht.ninv_w1;
+    }
+    int rc = TFB_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_fwd, fwd.size() * sizeof(tw_t))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_inv, inv.size() * sizeof(tw_t))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_pp, L * sizeof(PrimeParams))) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_fwd, fwd.data(), fwd.size() * sizeof(tw_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_inv, inv.data(), inv.size() * sizeof(tw_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_pp, pp.data(), L * sizeof(PrimeParams), cudaMemcpyHostToDevice)) != cudaSuccess)
+        rc = tfb_cuda_fail(e, "ctx_create table upload");
+    if (!rc) rc = build_garner(c);
+    if (!rc) rc = ntt_setup_device();
+    if (rc) {
+        std::string keep = g_err;
+        tfb_ctx_destroy(c);
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return TFB_OK;
+}
+
+int tfb_ctx_destroy(tfb_ctx* c) {
+    if (!c) return TFB_OK;
+    cudaSetDevice(c->device);
+    tfb_forget_ctx_pairs(c);
+    cudaFree(c->d_fwd);
+    cudaFree(c->d_inv);
+    cudaFree(c->d_pp);
+    cudaFree(c->d_ginv);
+    cudaFree(c->d_halfmr);
+    cudaFree(c->ws);
+    cudaFree(c->stage);
+    cudaFree(c->io);
+    delete c;
+    return TFB_OK;
+}
+
+int tfb_ctx_info(const tfb_ctx* c, uint32_t* N, uint32_t* L, uint64_t* q, uint64_t* psi) {
+    CHECK_CTX(c);
+    if (N) *N = c->N;
+    if (L) *L = c->L;
+    if (q) memcpy(q, c->q.data(), c->L * sizeof(u64));
+    if (psi) memcpy(psi, c->psi.data(), c->L * sizeof(u64));
+    return TFB_OK;
+}
+
+int tfb_malloc(tfb_ctx* c, size_t bytes, void** dptr) {
+    CHECK_CTX(c);
+    CHECK_PTR(dptr);
+    TFB_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); tfb_set_error("out of device memory"); return TFB_ENOMEM; }
+    return TFB_OK;
+}
+int tfb_free(tfb_ctx* c, void* dptr) {
+    CHECK_CTX(c);
+    TFB_CUDA(cudaFree(dptr));
+    return TFB_OK;
+}
+int tfb_memcpy_h2d(tfb_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {
+    CHECK_CTX(c);
+    TFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TFB_OK;
+}
+int tfb_memcpy_d2h(tfb_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {
+    CHECK_CTX(c);
+    TFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return TFB_OK;
+}
+int tfb_sync(tfb_ctx* c, void* stream) {
+    CHECK_CTX(c);
+    TFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return TFB_OK;
+}
+
+// ------------------------------------------------------------------ transforms
+int tfb_ntt_fwd(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    return launch_ntt(c, in, out, rows, false, (cudaStream_t)stream);
+}
+int tfb_ntt_inv(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    return launch_ntt(c, in, out, rows, true, (cudaStream_t)stream);
+}
+
+static int binop(tfb_ctx* c, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(b); CHECK_PTR(out);
+    return launch_binop(c, op, a, b, out, rows, (cudaStream_t)stream);
+}
+int tfb_add(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* s) { return binop(c, 0, a, b, out, rows, s); }
+int tfb_sub(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* s) { return binop(c, 1, a, b, out, rows, s); }
+int tfb_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* s) { return binop(c, 2, a, b, out, rows, s); }
+int tfb_neg(tfb_ctx* c, const uint64_t* a, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(out);
+    return launch_neg(c, a, out, rows, (cudaStream_t)stream);
+}
+int tfb_scalar_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* s_residues, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(out); CHECK_PTR(s_residues);
+    return launch_scalar_mul(c, a, s_residues, out, rows, (cudaStream_t)stream);
+}
+
+int tfb_ring_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(b); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)rows * c->N;
+    // the long-row NTT path uses c->ws itself, so keep our temporaries in `stage`
+    int rc = stage_reserve(c, 2 * words * sizeof(u64));
+    if (rc) return rc;
+    u64* A = (u64*)c->stage;
+    u64* B = A + words;
+    if ((rc = launch_ntt(c, a, A, rows, false, st))) return rc;
+    if ((rc = launch_ntt(c, b, B, rows, false, st))) return rc;
+    if ((rc = launch_binop(c, 2, A, B, A, rows, st))) return rc;
+    return launch_ntt(c, A, out, rows, true, st);
+}
+
+int tfb_galois(tfb_ctx* c, uint64_t g, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    return launch_galois(c, g, in, out, rows, (cudaStream_t)stream);
+}
+
+int tfb_rescale(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    if (in == out) { tfb_set_error("tfb_rescale cannot run in place"); return TFB_EINVAL; }
+    return launch_rescale(c, in, out, polys, (cudaStream_t)stream);
+}
+int tfb_crt_expand(tfb_ctx* c, uint64_t P, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    if (in == out) { tfb_set_error("tfb_crt_expand cannot run in place"); return TFB_EINVAL; }
+    return launch_crt_expand(c, P, in, out, polys, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------ ciphertext multiply
+static int ct_tensor_dev(tfb_ctx* c, const u64* c1, const u64* c2, u64* out, u64 batch, cudaStream_t st) {
+    const size_t poly = (size_t)c->L * c->N;
+    int rc = stage_reserve(c, 4 * batch * poly * sizeof(u64));
+    if (rc) return rc;
+    u64* A = (u64*)c->stage;
+    u64* B = A + 2 * batch * poly;
+    if ((rc = launch_ntt(c, c1, A, 2 * batch * c->L, false, st))) return rc;
+    if ((rc = launch_ntt(c, c2, B, 2 * batch * c->L, false, st))) return rc;
+    if ((rc = launch_tensor_dual(c, A, B, out, batch, st))) return rc;
+    return launch_ntt(c, out, out, 3 * batch * c->L, true, st);
+}
+
+int tfb_ct_tensor(tfb_ctx* c, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
+    return ct_tensor_dev(c, c1, c2, out, batch, (cudaStream_t)stream);
+}
+
+int tfb_bfv_switch(tfb_ctx* from, tfb_ctx* to, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(from); CHECK_CTX(to);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    if (in == out) { tfb_set_error("tfb_bfv_switch cannot run in place"); return TFB_EINVAL; }
+    return launch_base_switch(from, to, in, out, polys, (cudaStream_t)stream);
+}
+int tfb_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(cq); CHECK_CTX(cb);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    if (in == out) { tfb_set_error("tfb_bfv_contract cannot run in place"); return TFB_EINVAL; }
+    return launch_bfv_contract(cq, cb, t, in, out, polys, (cudaStream_t)stream);
+}
+
+// batch chunk so that the R_big intermediates (7 polys per pair) stay bounded
+static u64 bfv_chunk(const tfb_ctx* cb, u64 batch) {
+    const size_t per = 7 * (size_t)cb->L * cb->N * sizeof(u64);
+    u64 ch = (u64)((size_t)(3ull << 30) / per);
+    if (ch < 1) ch = 1;
+    return ch < batch ? ch : batch;
+}
+
+int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(cq); CHECK_CTX(cb);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
+    if (cq->N != cb->N) { tfb_set_error("bfv_mul: ring degrees differ"); return TFB_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t polyq = (size_t)cq->L * cq->N, polyb = (size_t)cb->L * cb->N;
+    const u64 ch = bfv_chunk(cb, batch);
+    int rc = ws_reserve(cb, 7 * ch * polyb * sizeof(u64));
+    if (rc) return rc;
+    u64* E1 = (u64*)cb->ws;
+    u64* E2 = E1 + 2 * ch * polyb;
+    u64* T = E2 + 2 * ch * polyb;
+    for (u64 b0 = 0; b0 < batch; b0 += ch) {
+        const u64 nb = batch - b0 < ch ? batch - b0 : ch;
+        if ((rc = launch_base_switch(cq, cb, c1 + b0 * 2 * polyq, E1, 2 * nb, st))) return rc;
+        if ((rc = launch_base_switch(cq, cb, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
+        if ((rc = launch_ntt(cb, E1, E1, 2 * nb * cb->L, false, st))) return rc;
+        if ((rc = launch_ntt(cb, E2, E2, 2 * nb * cb->L, false, st))) return rc;
+        if ((rc = launch_tensor_dual(cb, E1, E2, T, nb, st))) return rc;
+        if ((rc = launch_ntt(cb, T, T, 3 * nb * cb->L, true, st))) return rc;
+        if ((rc = launch_bfv_contract(cq, cb, t, T, out + b0 * 3 * polyq, 3 * nb, st))) return rc;
+    }
+    return TFB_OK;
+}
+
+// ------------------------------------------------------------------- keyswitch
+int tfb_keyswitch_digits(tfb_ctx* c, tfb_ctx* target, uint32_t w, const uint64_t* cend, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c); CHECK_CTX(target);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(cend); CHECK_PTR(out);
+    uint32_t D = c->L;
+    if (w) {
+        int rc = tfb_ndigits(c->q.data(), c->L, w, &D);
+        if (rc) return rc;
+    }
+    return launch_ks_digits(c, target, (int)w, cend, (u64)c->L * c->N, out, 0, D, batch, (cudaStream_t)stream);
+}
+
+int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
+                  uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(key_dual); CHECK_PTR(ct); CHECK_PTR(out);
+    if (comps != 2 && comps != 3) { tfb_set_error("keyswitch: ciphertext must have 2 or 3 components"); return TFB_EINVAL; }
+    uint32_t Dneed = c->L;
+    if (w) {
+        int rc = tfb_ndigits(c->q.data(), c->L, w, &Dneed);
+        if (rc) return rc;
+    }
+    if (D < Dneed) { tfb_set_error("keyswitch: evaluation key has too few digit components"); return TFB_EINVAL; }
+    tfb_ctx* r = ext ? ext : c;  // ring the accumulation happens in
+    if (ext) {
+        if (ext->N != c->N || ext->L != c->L + 1) { tfb_set_error("keyswitch: raised ring must be the ciphertext primes plus one special prime"); return TFB_EINVAL; }
+        for (u32 i = 0; i < c->L; i++)
+            if (ext->q[i] != c->q[i]) { tfb_set_error("keyswitch: raised ring must start with the ciphertext primes"); return TFB_EINVAL; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t polyr = (size_t)r->L * r->N, polyc = (size_t)c->L * c->N;
+    // digit chunk so the materialised digit polys stay below ~1 GiB
+    u32 dch = (u32)((size_t)(1ull << 30) / (batch * polyr * sizeof(u64)));
+    if (dch < 1) dch = 1;
+    if (dch > Dneed) dch = Dneed;
+    int rc = stage_reserve(r, (2 * batch * polyr + (size_t)dch * batch * polyr) * sizeof(u64));
+    if (rc) return rc;
+    u64* acc = (u64*)r->stage;
+    u64* dig = acc + 2 * batch * polyr;
+    const u64* cend = ct + (size_t)(comps - 1) * polyc;
+    for (u32 k0 = 0; k0 < Dneed; k0 += dch) {
+        const u32 dn = Dneed - k0 < dch ? Dneed - k0 : dch;
+        if ((rc = launch_ks_digits(c, r, (int)w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;
+        if ((rc = launch_ntt(r, dig, dig, (u64)batch * dn * r->L, false, st))) return rc;
+        if ((rc = launch_ks_accum(r, k0, dn, dig, key_dual, acc, k0 ? 1 : 0, batch, st))) return rc;
+    }
+    if ((rc = launch_ntt(r, acc, acc, 2 * batch * r->L, true, st))) return rc;
+    if (ext) return launch_ks_finish_raised(c, ext, ct, comps, acc, out, batch, st);
+    return launch_ks_finish(c, ct, comps, acc, out, batch, st);
+}
+
+// ---------------------------------------------------------- host-buffer variants
+#define H2D(dst, src, words) TFB_CUDA(cudaMemcpyAsync(dst, src, (words) * sizeof(u64), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, words) TFB_CUDA(cudaMemcpyAsync(dst, src, (words) * sizeof(u64), cudaMemcpyDeviceToHost, st))
+
+// host-call I/O buffer: a third growable allocation per context (ws and stage are
+// used by the device-side composites the host variants call into)
+static int io_buf(tfb_ctx* c, size_t words, u64** p) {
+    int rc = grow(&c->io, &c->io_bytes, words * sizeof(u64));
+    if (rc) return rc;
+    *p = (u64*)c->io;
+    return TFB_OK;
+}
+
+int tfb_ntt_fwd_host(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)rows * c->N;
+    u64* d;
+    int rc = io_buf(c, words, &d);
+    if (rc) return rc;
+    H2D(d, in, words);
+    if ((rc = launch_ntt(c, d, d, rows, false, st))) return rc;
+    D2H(out, d, words);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_ntt_inv_host(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)rows * c->N;
+    u64* d;
+    int rc = io_buf(c, words, &d);
+    if (rc) return rc;
+    H2D(d, in, words);
+    if ((rc = launch_ntt(c, d, d, rows, true, st))) return rc;
+    D2H(out, d, words);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_ring_mul_host(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
+    CHECK_CTX(c); CHECK_ROWS(c, rows);
+    if (!rows) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(b); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)rows * c->N;
+    u64* d;
+    int rc = io_buf(c, 2 * words, &d);
+    if (rc) return rc;
+    H2D(d, a, words);
+    H2D(d + words, b, words);
+    if ((rc = tfb_ring_mul(c, d, d + words, d, rows, stream))) return rc;
+    D2H(out, d, words);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_ct_tensor_host(tfb_ctx* c, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t poly = (size_t)c->L * c->N;
+    u64* d;
+    int rc = io_buf(c, 7 * batch * poly, &d);
+    if (rc) return rc;
+    u64 *d1 = d, *d2 = d + 2 * batch * poly, *dout = d + 4 * batch * poly;
+    H2D(d1, c1, 2 * batch * poly);
+    H2D(d2, c2, 2 * batch * poly);
+    if ((rc = ct_tensor_dev(c, d1, d2, dout, batch, st))) return rc;
+    D2H(out, dout, 3 * batch * poly);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_bfv_mul_host(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(cq); CHECK_CTX(cb);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t poly = (size_t)cq->L * cq->N;
+    u64* d;
+    int rc = io_buf(cq, 7 * batch * poly, &d);
+    if (rc) return rc;
+    u64 *d1 = d, *d2 = d + 2 * batch * poly, *dout = d + 4 * batch * poly;
+    H2D(d1, c1, 2 * batch * poly);
+    H2D(d2, c2, 2 * batch * poly);
+    if ((rc = tfb_bfv_mul(cq, cb, t, d1, d2, dout, batch, stream))) return rc;
+    D2H(out, dout, 3 * batch * poly);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_rescale_host(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pin = (size_t)c->L * c->N, pout = (size_t)(c->L - 1) * c->N;
+    u64* d;
+    int rc = io_buf(c, polys * (pin + pout), &d);
+    if (rc) return rc;
+    H2D(d, in, polys * pin);
+    if ((rc = launch_rescale(c, d, d + polys * pin, polys, st))) return rc;
+    D2H(out, d + polys * pin, polys * pout);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+
+}  // extern "C"
+

@@ -1,0 +1,87 @@
+// Internal declarations shared by the .cu translation units of libtoyfhe_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/toyfhe_b200.h"
+#include "modarith.cuh"
+
+struct PrimeParams {
+    PrimeConst pc;
+    tw_t ninv;     // N^-1
+    tw_t ninv_w1;  // N^-1 * psi^-brev(1)
+};
+
+struct tfb_ctx {
+    int device;
+    u32 N, logN, L;
+    std::vector<u64> q, psi;
+    tw_t* d_fwd;      // [L][N]
+    tw_t* d_inv;      // [L][N]
+    PrimeParams* d_pp;  // [L]
+    // Garner constants for conversions *from* this basis (rns_kernels.cu: build_garner)
+    tw_t* d_ginv;     // [L]: Shoup pair of (prod_{k<i} q_k)^-1 mod q_i
+    u64* d_halfmr;    // allocation: [L*L] Garner matrix, then [L] mixed-radix digits of floor(Q/2)
+    std::vector<u64> halfmr;
+    bool conv_ok;     // basis small enough for 128-bit lazy accumulation in conversions
+    // scratch (device) and staging (device, for the *_host entry points)
+    void* ws;
+    size_t ws_bytes;
+    void* stage;
+    size_t stage_bytes;
+    void* io;
+    size_t io_bytes;
+};
+
+void tfb_set_error(const std::string& msg);
+int tfb_cuda_fail(cudaError_t e, const char* what);
+#define TFB_CUDA(x)                                                \
+    do {                                                           \
+        cudaError_t _e = (x);                                      \
+        if (_e != cudaSuccess) return tfb_cuda_fail(_e, #x);       \
+    } while (0)
+
+
+int ws_reserve(tfb_ctx* c, size_t bytes);
+int stage_reserve(tfb_ctx* c, size_t bytes);
+
+// per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+enum ProfClass {
+    PC_NTT_FWD = 0, PC_NTT_INV, PC_NTT_OTHER, PC_ELEMENTWISE, PC_TENSOR, PC_BASE_SWITCH, PC_BFV_CONTRACT,
+    PC_KS_DIGITS, PC_KS_ACCUM, PC_KS_FINISH, PC_LEVEL, PC_COUNT
+};
+struct ProfScope {
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t stop;
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+};
+
+// ntt_kernels.cu
+int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
+unsigned long long tfb_launch_count();
+void tfb_count_launch(int n = 1);
+
+// rns_kernels.cu
+int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 rows, cudaStream_t st);
+int launch_neg(tfb_ctx* c, const u64* a, u64* out, u64 rows, cudaStream_t st);
+int launch_scalar_mul(tfb_ctx* c, const u64* a, const u64* s_host, u64* out, u64 rows, cudaStream_t st);
+int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 batch, cudaStream_t st);
+int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStream_t st);
+int launch_rescale(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_crt_expand(tfb_ctx* c, u64 P, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct_stride, u64* out, u32 k0, u32 Dn,
+                     u64 batch, cudaStream_t st);
+int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
+                    cudaStream_t st);
+int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st);
+int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch,
+                            cudaStream_t st);
+int build_garner(tfb_ctx* c);
+void tfb_forget_ctx_pairs(const tfb_ctx* c);
+int ntt_setup_device();

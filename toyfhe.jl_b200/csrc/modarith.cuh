@@ -1,0 +1,142 @@
+// Word-size modular arithmetic for the sm_100a negacyclic-NTT engine.
+//
+// Replaces GaloisFields.jl PrimeField `* + - inv ^` (widemul + rem) on the hot
+// path of pow2_cyc_rings.jl / crt.jl with Shoup (precomputed-quotient) and
+// Barrett multiplication.  All residues are canonical in [0,q) at kernel
+// boundaries; inside the butterfly ladders values are lazily kept in [0,4q)
+// (Harvey), which needs q < 2^62.
+#pragma once
+#include <cstdint>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef unsigned __int128 u128;
+
+#define TFB_MAX_L 64  // max RNS primes per context
+
+#ifndef __CUDACC__
+#define __align__(n) __attribute__((aligned(n)))
+#endif
+
+// (w, w') pair: w' = floor(w * 2^64 / q)
+struct __align__(16) tw_t {
+    u64 w, wp;
+};
+
+struct PrimeConst {
+    u64 q;        // modulus
+    u64 q2;       // 2q
+    u64 br_hi;    // floor(2^128 / q) high word
+    u64 br_lo;    // floor(2^128 / q) low word
+};
+
+#ifdef __CUDACC__
+#define TFB_HD __host__ __device__ __forceinline__
+#define TFB_D __host__ __device__ __forceinline__
+#else
+#define TFB_HD inline
+#define TFB_D inline
+#endif
+
+// high 64 bits of a 64x64 product (device: IMAD.WIDE ladder; host: __int128 --
+// the host path exists only so tests can emulate the kernels' index logic on CPU)
+TFB_D u64 mulhi64(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (u64)(((u128)a * b) >> 64);
+#endif
+}
+
+// x*w mod q, lazily in [0,2q); valid for ANY 64-bit x (Harvey/Shoup).
+TFB_D u64 shoup_lazy(u64 x, u64 w, u64 wp, u64 q) {
+    u64 h = mulhi64(x, wp);
+    return x * w - h * q;
+}
+TFB_D u64 shoup_lazy(u64 x, tw_t t, u64 q) { return shoup_lazy(x, t.w, t.wp, q); }
+
+// conditional subtract: x in [0,2m) -> [0,m)
+TFB_D u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
+
+TFB_D u64 shoup_full(u64 x, u64 w, u64 wp, u64 q) { return csub(shoup_lazy(x, w, wp, q), q); }
+
+// a*b mod q for arbitrary a,b < 2^64 with a*b < q*2^64 (always true for a,b<q<2^63):
+// Barrett with ratio = floor(2^128/q) (two words), result canonical.
+TFB_D u64 barrett_mul(u64 a, u64 b, const PrimeConst& pc) {
+    u64 z0 = a * b, z1 = mulhi64(a, b);
+    // estimate floor(z * ratio / 2^128), low 64 bits only
+    u64 c = mulhi64(z0, pc.br_lo);
+    u64 t0 = z0 * pc.br_hi, t1 = mulhi64(z0, pc.br_hi);
+    u64 s = t0 + c;
+    u64 carry = s < t0;
+    u64 r1 = t1 + carry;
+    u64 u0 = z1 * pc.br_lo, u1 = mulhi64(z1, pc.br_lo);
+    u64 s2 = s + u0;
+    u64 carry2 = s2 < u0;
+    u64 qhat = z1 * pc.br_hi + r1 + u1 + carry2;
+    u64 r = z0 - qhat * pc.q;
+    // qhat underestimates by at most 2
+    r = csub(r, pc.q2);
+    return csub(r, pc.q);
+}
+
+// reduce a 128-bit value (hi,lo) < q * 2^64 modulo q (canonical)
+TFB_D u64 barrett_red128(u64 z1, u64 z0, const PrimeConst& pc) {
+    u64 c = mulhi64(z0, pc.br_lo);
+    u64 t0 = z0 * pc.br_hi, t1 = mulhi64(z0, pc.br_hi);
+    u64 s = t0 + c;
+    u64 carry = s < t0;
+    u64 r1 = t1 + carry;
+    u64 u0 = z1 * pc.br_lo, u1 = mulhi64(z1, pc.br_lo);
+    u64 s2 = s + u0;
+    u64 carry2 = s2 < u0;
+    u64 qhat = z1 * pc.br_hi + r1 + u1 + carry2;
+    u64 r = z0 - qhat * pc.q;
+    r = csub(r, pc.q2);
+    return csub(r, pc.q);
+}
+
+// x mod q for a single word x (canonical)
+TFB_D u64 barrett_red64(u64 x, const PrimeConst& pc) {
+    u64 qhat = mulhi64(x, pc.br_hi);  // floor(x*ratio/2^128) ~ hi(x * br_hi) (under by <=2)
+    u64 r = x - qhat * pc.q;
+    r = csub(r, pc.q2);
+    return csub(r, pc.q);
+}
+
+TFB_D u64 add_mod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+TFB_D u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+TFB_D u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// ----------------------------------------------------------------- host side
+static inline u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)((u128)a * b % q); }
+static inline u64 h_powmod(u64 a, u64 e, u64 q) {
+    u64 r = 1 % q;
+    a %= q;
+    while (e) {
+        if (e & 1) r = h_mulmod(r, a, q);
+        a = h_mulmod(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+static inline u64 h_invmod(u64 a, u64 q) { return h_powmod(a, q - 2, q); }
+static inline u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static inline tw_t h_tw(u64 w, u64 q) {
+    tw_t t;
+    t.w = w;
+    t.wp = h_shoup(w, q);
+    return t;
+}
+static inline PrimeConst h_prime_const(u64 q) {
+    PrimeConst pc;
+    pc.q = q;
+    pc.q2 = 2 * q;
+    // floor(2^128 / q): long division of 2^128 by q
+    u128 hi = ((u128)1 << 64) / q;            // floor(2^64 / q)  (fits: q >= 2)
+    u128 rem = ((u128)1 << 64) % q;
+    u128 lo = (rem << 64) / q;
+    pc.br_hi = (u64)hi;
+    pc.br_lo = (u64)lo;
+    return pc;
+}

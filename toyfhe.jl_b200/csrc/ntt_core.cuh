@@ -1,0 +1,240 @@
+// Per-thread bodies of the row-resident negacyclic NTT kernels (N = 2^(10+R),
+// R = 0..4: one CTA of N/32 threads per prime-row, 32 residues per thread in
+// registers, two shared-memory exchanges).
+//
+// Computes exactly what pow2_cyc_rings.jl:295-303 (nntt) and :308-318 (inntt)
+// define -- c^[k] = sum_j c[j] psi^(j(2k+1)), natural order in and out -- but as a
+// merged (psi folded into the twiddles) Cooley-Tukey / Gentleman-Sande ladder
+// with Harvey lazy butterflies; FourierTransforms.jl's CTPlan and the per-call
+// twiddle rebuild (pow2_cyc_rings.jl:298-301) have no counterpart here.
+//
+// Position bits of a residue inside the row: p = (a : 5 | b : 5 | c : R).
+//   pass 1 (stages 1..5)      thread t=(b,c) holds a = 0..31     (stride N/32)
+//   pass 2 (stages 6..10)     thread (a,c)   holds b = 0..31
+//   pass 3 (stages 11..10+R)  thread (warp w, lane l) holds, for a = brev5(l),
+//                             the G = 32/2^R groups b = brev5(w*G+g), all c.
+// The merged CT ladder leaves c^[brev(p)] at position p; with the pass-3 mapping
+// the natural index is k = brevR(c)<<10 | (w*G+g)<<5 | l, so a warp stores 32
+// consecutive words: natural-order output costs no extra permutation pass.
+//
+// The functions are __host__ __device__ so tests can run the *same* index logic
+// thread-by-thread on the CPU (tests/emu); the product only uses them from the
+// kernels in ntt_kernels.cu.
+#pragma once
+#include "modarith.cuh"
+
+template <int R>
+struct NttGeo {
+    static constexpr int LOGN = 10 + R;
+    static constexpr u32 N = 1u << LOGN;
+    static constexpr u32 T = N / 32;   // threads per row
+    static constexpr u32 RS = 1u << R; // pass-3 group size
+    static constexpr u32 G = 32 / RS;  // pass-3 groups per thread
+};
+
+TFB_HD u32 brev_bits(u32 x, int bits) {
+    if (bits == 0) return 0;
+#ifdef __CUDA_ARCH__
+    return __brev(x) >> (32 - bits);
+#else
+    u32 r = 0;
+    for (int i = 0; i < bits; i++)
+        if (x >> i & 1) r |= 1u << (bits - 1 - i);
+    return r;
+#endif
+}
+
+// shared-memory slot of position (a, idx=(b,c)); the XOR keeps all three access
+// patterns (lanes along t, along (a_lo,c), along a) on distinct 8-byte banks.
+template <int R>
+TFB_HD u32 swz(u32 a, u32 idx) {
+    return a * NttGeo<R>::T + (idx ^ (a >> 1));
+}
+
+// Harvey lazy butterflies.  CT: X,Y in [0,4q) -> [0,4q).  GS: X,Y in [0,2q) -> [0,2q).
+TFB_HD void ct_bfly(u64& X, u64& Y, const tw_t w, const u64 q, const u64 q2) {
+    u64 x = csub(X, q2);
+    u64 t = shoup_lazy(Y, w.w, w.wp, q);
+    X = x + t;
+    Y = x - t + q2;
+}
+TFB_HD void gs_bfly(u64& X, u64& Y, const tw_t w, const u64 q, const u64 q2) {
+    u64 s = X + Y;
+    u64 d = X - Y + q2;
+    X = csub(s, q2);
+    Y = shoup_lazy(d, w.w, w.wp, q);
+}
+
+// LV radix-2 CT levels over CNT=2^LV consecutive registers x[off..off+CNT);
+// level u (1..LV) block j uses twiddle tw[base(u) + j], base(u) = (lead << (u-1)) + ofs(u)
+// where the caller folds everything into `tb[u-1]`.
+template <int LV>
+TFB_HD void ct_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const u64 q, const u64 q2) {
+#pragma unroll
+    for (int u = 1; u <= LV; u++) {
+        const int half = (1 << LV) >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << (u - 1)); j++) {
+            const tw_t w = tw[tb[u - 1] + j];
+#pragma unroll
+            for (int k = 0; k < half; k++) ct_bfly(x[j * 2 * half + k], x[j * 2 * half + k + half], w, q, q2);
+        }
+    }
+}
+// inverse order of the same ladder (levels LV..FIRST), GS butterflies
+template <int LV, int FIRST>
+TFB_HD void gs_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const u64 q, const u64 q2) {
+#pragma unroll
+    for (int u = LV; u >= FIRST; u--) {
+        const int half = (1 << LV) >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << (u - 1)); j++) {
+            const tw_t w = tw[tb[u - 1] + j];
+#pragma unroll
+            for (int k = 0; k < half; k++) gs_bfly(x[j * 2 * half + k], x[j * 2 * half + k + half], w, q, q2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward
+// `in` points at the sub-block (Nsub = N contiguous positions); s0 = stages
+// already applied to the whole row (0 unless the row is longer than 2^14),
+// blk = index of this sub-block at level s0.
+template <int R>
+TFB_HD void fwd_phaseA(u64* x, const u64* __restrict__ in, u64* smem, const tw_t* __restrict__ tw,
+                       const u64 q, const u32 t, const u32 s0, const u32 blk) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+#pragma unroll
+    for (int a = 0; a < 32; a++) x[a] = in[a * Geo::T + t];
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
+    ct_levels<5>(x, tw, tb, q, q2);
+#pragma unroll
+    for (int a = 0; a < 32; a++) smem[swz<R>(a, t)] = x[a];
+}
+
+template <int R>
+TFB_HD void fwd_phaseB(u64* x, u64* smem, const tw_t* __restrict__ tw, const u64 q, const u32 t,
+                       const u32 s0, const u32 blk) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+    const u32 a2 = t >> R, c2 = t & (Geo::RS - 1);
+#pragma unroll
+    for (int b = 0; b < 32; b++) x[b] = smem[swz<R>(a2, b * Geo::RS + c2)];
+    u32 tb[5];
+#pragma unroll
+    for (int u = 1; u <= 5; u++) tb[u - 1] = (1u << (s0 + 4 + u)) + (blk << (4 + u)) + (a2 << (u - 1));
+    ct_levels<5>(x, tw, tb, q, q2);
+#pragma unroll
+    for (int b = 0; b < 32; b++) smem[swz<R>(a2, b * Geo::RS + c2)] = x[b];
+}
+
+// out points at the row base; the natural index of local position p is
+// (brev(p) << s0) + brev_s0(blk)
+template <int R>
+TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_t* __restrict__ tw,
+                       const u64 q, const u32 t, const u32 s0, const u32 blk) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+    const u32 w = t >> 5, lane = t & 31;
+    const u32 a3 = brev_bits(lane, 5);
+    const u32 oblk = brev_bits(blk, (int)s0);
+#pragma unroll
+    for (int g = 0; g < (int)Geo::G; g++) {
+        const u32 k2 = w * Geo::G + g;
+        const u32 b3 = brev_bits(k2, 5);
+#pragma unroll
+        for (int c = 0; c < (int)Geo::RS; c++) x[g * Geo::RS + c] = smem[swz<R>(a3, b3 * Geo::RS + c)];
+        if (R > 0) {
+            u32 tb[R > 0 ? R : 1];
+#pragma unroll
+            for (int u = 1; u <= R; u++)
+                tb[u - 1] = (1u << (s0 + 9 + u)) + (blk << (9 + u)) + ((a3 * 32 + b3) << (u - 1));
+            ct_levels<R>(x + g * Geo::RS, tw, tb, q, q2);
+        }
+#pragma unroll
+        for (int c = 0; c < (int)Geo::RS; c++) {
+            const u32 kl = (brev_bits((u32)c, R) << 10) | (k2 << 5) | lane;
+            u64 v = x[g * Geo::RS + c];
+            v = csub(v, q2);
+            v = csub(v, q);
+            out[((u64)kl << s0) + oblk] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ inverse
+// itw = inverse table (psi^-brev(idx)); scale: N^-1 folded into the last level
+// when s0 == 0 (tn = Shoup pair of N^-1, twn = Shoup pair of N^-1 * itw[1]).
+template <int R>
+TFB_HD void inv_phaseC(u64* x, const u64* __restrict__ in, u64* smem, const tw_t* __restrict__ itw,
+                       const u64 q, const u32 t, const u32 s0, const u32 blk) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+    const u32 w = t >> 5, lane = t & 31;
+    const u32 a3 = brev_bits(lane, 5);
+    const u32 oblk = brev_bits(blk, (int)s0);
+#pragma unroll
+    for (int g = 0; g < (int)Geo::G; g++) {
+        const u32 k2 = w * Geo::G + g;
+        const u32 b3 = brev_bits(k2, 5);
+#pragma unroll
+        for (int c = 0; c < (int)Geo::RS; c++) {
+            const u32 kl = (brev_bits((u32)c, R) << 10) | (k2 << 5) | lane;
+            x[g * Geo::RS + c] = in[((u64)kl << s0) + oblk];
+        }
+        if (R > 0) {
+            u32 tb[R > 0 ? R : 1];
+#pragma unroll
+            for (int u = 1; u <= R; u++)
+                tb[u - 1] = (1u << (s0 + 9 + u)) + (blk << (9 + u)) + ((a3 * 32 + b3) << (u - 1));
+            gs_levels<R, 1>(x + g * Geo::RS, itw, tb, q, q2);
+        }
+#pragma unroll
+        for (int c = 0; c < (int)Geo::RS; c++) smem[swz<R>(a3, b3 * Geo::RS + c)] = x[g * Geo::RS + c];
+    }
+}
+
+template <int R>
+TFB_HD void inv_phaseB(u64* x, u64* smem, const tw_t* __restrict__ itw, const u64 q, const u32 t,
+                       const u32 s0, const u32 blk) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+    const u32 a2 = t >> R, c2 = t & (Geo::RS - 1);
+#pragma unroll
+    for (int b = 0; b < 32; b++) x[b] = smem[swz<R>(a2, b * Geo::RS + c2)];
+    u32 tb[5];
+#pragma unroll
+    for (int u = 1; u <= 5; u++) tb[u - 1] = (1u << (s0 + 4 + u)) + (blk << (4 + u)) + (a2 << (u - 1));
+    gs_levels<5, 1>(x, itw, tb, q, q2);
+#pragma unroll
+    for (int b = 0; b < 32; b++) smem[swz<R>(a2, b * Geo::RS + c2)] = x[b];
+}
+
+template <int R>
+TFB_HD void inv_phaseA(u64* x, u64* __restrict__ out, const u64* smem, const tw_t* __restrict__ itw,
+                       const u64 q, const u32 t, const u32 s0, const u32 blk, const tw_t tn, const tw_t twn) {
+    typedef NttGeo<R> Geo;
+    const u64 q2 = 2 * q;
+#pragma unroll
+    for (int a = 0; a < 32; a++) x[a] = smem[swz<R>(a, t)];
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
+    if (s0 == 0) {
+        gs_levels<5, 2>(x, itw, tb, q, q2);
+        // last level with N^-1 folded in (both outputs pass through a Shoup product)
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const u64 U = x[k], V = x[k + 16];
+            x[k] = shoup_lazy(U + V, tn.w, tn.wp, q);
+            x[k + 16] = shoup_lazy(U - V + q2, twn.w, twn.wp, q);
+        }
+    } else {
+        gs_levels<5, 1>(x, itw, tb, q, q2);
+    }
+#pragma unroll
+    for (int a = 0; a < 32; a++) out[a * Geo::T + t] = csub(x[a], q);
+}

@@ -1,0 +1,239 @@
+// Negacyclic NTT kernels for sm_100a: the engine's replacement for
+// NTT.nntt / NTT.inntt (pow2_cyc_rings.jl:295-318) and their per-prime RNS
+// dispatch (crt.jl:247-267).  Rows are laid out [..][L][N] (residue-major, the
+// StructArray layout); row r belongs to prime r % L.
+//
+//  * N = 2^10 .. 2^14 : one CTA per row, whole row resident on chip
+//                        (32 residues per thread in registers, two swizzled
+//                        shared-memory exchanges) -- ntt_core.cuh.
+//  * N = 2^15, 2^16   : the top s0 = logN-14 levels run as global-memory stage
+//                        kernels, the rest as 2^s0 row-resident sub-blocks.
+//  * N < 2^10         : small shared-memory kernel (test-sized rings of the
+//                        reference's own unit tests: N = 16, 32, ...).
+#include <atomic>
+
+#include "engine.h"
+#include "ntt_core.cuh"
+
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long tfb_launch_count() { return g_launches.load(); }
+void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
+
+// ------------------------------------------------------------ row-resident
+template <int R>
+__global__ void __launch_bounds__(NttGeo<R>::T, 1)
+ntt_fwd_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                   const PrimeParams* __restrict__ pp, const u32 L, const u32 s0) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 t = threadIdx.x;
+    const u64 row = (u64)blockIdx.x >> s0;
+    const u32 blk = blockIdx.x & ((1u << s0) - 1);
+    const u32 prime = (u32)(row % L);
+    const u64 nrow = (u64)Geo::N << s0;
+    const tw_t* tw = tw_all + (u64)prime * nrow;
+    const u64 q = pp[prime].pc.q;
+    u64 x[32];
+    fwd_phaseA<R>(x, in + row * nrow + (u64)blk * Geo::N, smem, tw, q, t, s0, blk);
+    __syncthreads();
+    fwd_phaseB<R>(x, smem, tw, q, t, s0, blk);
+    __syncthreads();
+    fwd_phaseC<R>(x, out + row * nrow, smem, tw, q, t, s0, blk);
+}
+
+template <int R>
+__global__ void __launch_bounds__(NttGeo<R>::T, 1)
+ntt_inv_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                   const PrimeParams* __restrict__ pp, const u32 L, const u32 s0) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 t = threadIdx.x;
+    const u64 row = (u64)blockIdx.x >> s0;
+    const u32 blk = blockIdx.x & ((1u << s0) - 1);
+    const u32 prime = (u32)(row % L);
+    const u64 nrow = (u64)Geo::N << s0;
+    const tw_t* tw = tw_all + (u64)prime * nrow;
+    const PrimeParams P = pp[prime];
+    const u64 q = P.pc.q;
+    u64 x[32];
+    inv_phaseC<R>(x, in + row * nrow, smem, tw, q, t, s0, blk);
+    __syncthreads();
+    inv_phaseB<R>(x, smem, tw, q, t, s0, blk);
+    __syncthreads();
+    inv_phaseA<R>(x, out + row * nrow + (u64)blk * Geo::N, smem, tw, q, t, s0, blk, P.ninv, P.ninv_w1);
+}
+
+// ------------------------------------------------- global stages (N > 2^14)
+// forward level s (1-based) over whole rows, canonical in -> canonical out
+__global__ void ntt_fwd_stage_kernel(const u64* __restrict__ in, u64* __restrict__ out,
+                                     const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ pp,
+                                     const u32 L, const u32 logN, const u32 s, const u64 total) {
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const u64 row = gid >> (logN - 1);
+    const u32 i = (u32)(gid & ((1ull << (logN - 1)) - 1));
+    const u32 prime = (u32)(row % L);
+    const u64 q = pp[prime].pc.q;
+    const u32 half = 1u << (logN - s);
+    const u32 j = i >> (logN - s), k = i & (half - 1);
+    const u64 p0 = (row << logN) + ((u64)j << (logN - s + 1)) + k;
+    const tw_t w = tw_all[((u64)prime << logN) + (1u << (s - 1)) + j];
+    const u64 X = in[p0], T = shoup_full(in[p0 + half], w.w, w.wp, q);
+    out[p0] = add_mod(X, T, q);
+    out[p0 + half] = sub_mod(X, T, q);
+}
+// inverse level s; level 1 folds in N^-1
+__global__ void ntt_inv_stage_kernel(const u64* __restrict__ in, u64* __restrict__ out,
+                                     const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ pp,
+                                     const u32 L, const u32 logN, const u32 s, const u64 total) {
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const u64 row = gid >> (logN - 1);
+    const u32 i = (u32)(gid & ((1ull << (logN - 1)) - 1));
+    const u32 prime = (u32)(row % L);
+    const PrimeParams P = pp[prime];
+    const u64 q = P.pc.q;
+    const u32 half = 1u << (logN - s);
+    const u32 j = i >> (logN - s), k = i & (half - 1);
+    const u64 p0 = (row << logN) + ((u64)j << (logN - s + 1)) + k;
+    const tw_t w = tw_all[((u64)prime << logN) + (1u << (s - 1)) + j];
+    const u64 X = in[p0], Y = in[p0 + half];
+    u64 S = add_mod(X, Y, q), D = sub_mod(X, Y, q);
+    if (s == 1) {
+        S = shoup_full(S, P.ninv.w, P.ninv.wp, q);
+        D = shoup_full(D, P.ninv_w1.w, P.ninv_w1.wp, q);
+    } else {
+        D = shoup_full(D, w.w, w.wp, q);
+    }
+    out[p0] = S;
+    out[p0 + half] = D;
+}
+
+// ------------------------------------------------------ small rows (N < 2^10)
+__global__ void ntt_small_kernel(const u64* __restrict__ in, u64* __restrict__ out,
+                                 const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ pp,
+                                 const u32 L, const u32 logN, const int inverse) {
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 N = 1u << logN;
+    const u64 row = blockIdx.x;
+    const u32 prime = (u32)(row % L);
+    const PrimeParams P = pp[prime];
+    const u64 q = P.pc.q, q2 = 2 * q;
+    const tw_t* tw = tw_all + ((u64)prime << logN);
+    const u64* src = in + (row << logN);
+    u64* dst = out + (row << logN);
+    if (!inverse) {
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x) smem[i] = src[i];
+        __syncthreads();
+        for (u32 s = 1; s <= logN; s++) {
+            const u32 half = 1u << (logN - s);
+            for (u32 i = threadIdx.x; i < N / 2; i += blockDim.x) {
+                const u32 j = i >> (logN - s), k = i & (half - 1);
+                const u32 p0 = (j << (logN - s + 1)) + k;
+                ct_bfly(smem[p0], smem[p0 + half], tw[(1u << (s - 1)) + j], q, q2);
+            }
+            __syncthreads();
+        }
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x)
+            dst[brev_bits(i, (int)logN)] = csub(csub(smem[i], q2), q);
+    } else {
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x) smem[i] = src[brev_bits(i, (int)logN)];
+        __syncthreads();
+        for (u32 s = logN; s >= 1; s--) {
+            const u32 half = 1u << (logN - s);
+            for (u32 i = threadIdx.x; i < N / 2; i += blockDim.x) {
+                const u32 j = i >> (logN - s), k = i & (half - 1);
+                const u32 p0 = (j << (logN - s + 1)) + k;
+                gs_bfly(smem[p0], smem[p0 + half], tw[(1u << (s - 1)) + j], q, q2);
+            }
+            __syncthreads();
+        }
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x)
+            dst[i] = shoup_full(smem[i], P.ninv.w, P.ninv.wp, q);
+    }
+}
+
+// ------------------------------------------------------------------ launcher
+template <int R>
+static int launch_row(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st) {
+    typedef NttGeo<R> Geo;
+    const size_t smem = (size_t)Geo::N * sizeof(u64);
+    const u64 blocks = rows << s0;
+    if (blocks > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+    if (inverse)
+        { ProfScope ps(PC_NTT_INV, st); ntt_inv_row_kernel<R><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_inv, c->d_pp, c->L, s0); }
+    else
+        { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+template <int R>
+static int setup_row() {
+    const int smem = (int)(NttGeo<R>::N * sizeof(u64));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_inv_row_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_row_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return TFB_OK;
+}
+// opt in to >48 KiB dynamic shared memory on the current device (called per context)
+int ntt_setup_device() {
+    int rc;
+    if ((rc = setup_row<0>())) return rc;
+    if ((rc = setup_row<1>())) return rc;
+    if ((rc = setup_row<2>())) return rc;
+    if ((rc = setup_row<3>())) return rc;
+    return setup_row<4>();
+}
+
+static int launch_row_dispatch(tfb_ctx* c, int R, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st) {
+    switch (R) {
+        case 0: return launch_row<0>(c, in, out, rows, inverse, s0, st);
+        case 1: return launch_row<1>(c, in, out, rows, inverse, s0, st);
+        case 2: return launch_row<2>(c, in, out, rows, inverse, s0, st);
+        case 3: return launch_row<3>(c, in, out, rows, inverse, s0, st);
+        case 4: return launch_row<4>(c, in, out, rows, inverse, s0, st);
+    }
+    tfb_set_error("internal: bad R");
+    return TFB_EINVAL;
+}
+
+int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st) {
+    if (rows == 0) return TFB_OK;
+    const u32 logN = c->logN;
+    if (logN < 10) {
+        const u32 N = c->N;
+        unsigned threads = N / 2 < 32 ? 32 : (N / 2 > 512 ? 512 : N / 2);
+        if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+        { ProfScope ps(PC_NTT_OTHER, st); ntt_small_kernel<<<(unsigned)rows, threads, (size_t)N * sizeof(u64), st>>>(
+            in, out, inverse ? c->d_inv : c->d_fwd, c->d_pp, c->L, logN, inverse ? 1 : 0); }
+        TFB_CUDA(cudaGetLastError());
+        return TFB_OK;
+    }
+    if (logN <= 14) return launch_row_dispatch(c, (int)logN - 10, in, out, rows, inverse, 0, st);
+    if (logN > 16) { tfb_set_error("N > 2^16 is not supported"); return TFB_EUNSUPPORTED; }
+    // long rows: s0 global levels + row-resident sub-blocks, through scratch
+    const u32 s0 = logN - 14;
+    const size_t bytes = (size_t)rows * c->N * sizeof(u64);
+    int rc = ws_reserve(c, bytes);
+    if (rc) return rc;
+    u64* tmp = (u64*)c->ws;
+    const u64 total = rows << (logN - 1);
+    const unsigned tb = 256;
+    const unsigned nb = (unsigned)((total + tb - 1) / tb);
+    if (!inverse) {
+        const u64* src = in;
+        for (u32 s = 1; s <= s0; s++) {
+            { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
+            src = tmp;
+        }
+        TFB_CUDA(cudaGetLastError());
+        return launch_row_dispatch(c, 4, tmp, out, rows, false, s0, st);
+    }
+    rc = launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
+    if (rc) return rc;
+    for (u32 s = s0; s >= 1; s--) {
+        { ProfScope ps(PC_NTT_OTHER, st); ntt_inv_stage_kernel<<<nb, tb, 0, st>>>(tmp, s == 1 ? out : tmp, c->d_inv, c->d_pp, c->L, logN, s, total); }
+    }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}

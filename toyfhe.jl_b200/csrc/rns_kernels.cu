@@ -1,0 +1,730 @@
+// RNS / CRT kernels: the engine's replacement for the per-coefficient Julia code
+// of crt.jl (CRTEncoded + - *, CRTExpand, modswitch), bfv.jl (switch/switchel,
+// multround), rlwe_she.jl (digit decomposition, key accumulation) and
+// pow2_cyc_rings.jl:321-329 (apply_galois_element).
+//
+// Where the reference reconstructs a BigInt per coefficient (crt.jl:105-112) the
+// engine stays in word arithmetic: an exact Garner mixed-radix conversion
+//     X = d_0 + d_1 q_0 + d_2 q_0 q_1 + ...,   0 <= d_i < q_i
+// gives comparisons with Q/2 (centred lift, signedmod.jl:12-19), residues modulo
+// any other prime, exact division by Q (round-half-away, div_hacks.jl:120-135) and
+// base-2^w digits, all bit-identical to the BigInt path.
+//
+// Layout everywhere: u64 [..][L][N], thread index runs along N (coalesced).
+#include <map>
+
+#include "engine.h"
+
+#define MAXD 32  // max primes in a basis that takes part in base conversion
+
+// 128-bit accumulator helpers ------------------------------------------------
+struct acc128 {
+    u64 lo, hi;
+};
+__device__ __forceinline__ void mac128(acc128& a, u64 x, u64 y) {
+    u64 lo = x * y, hi = __umul64hi(x, y);
+    a.lo += lo;
+    a.hi += hi + (a.lo < lo);
+}
+// full reduction of a 128-bit value modulo q (any size of z)
+__device__ __forceinline__ u64 red128_full(acc128 a, const PrimeConst& pc) {
+    u64 h = barrett_red64(a.hi, pc);
+    return barrett_red128(h, a.lo, pc);
+}
+
+// ------------------------------------------------------------- elementwise
+template <int OP>
+__global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ b,
+                             ulonglong2* __restrict__ out, const PrimeParams* __restrict__ pp, const u32 L,
+                             const u32 logN, const u64 total2) {
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 row = idx >> (logN - 1);
+        const PrimeConst pc = pp[row % L].pc;
+        const ulonglong2 x = a[idx], y = b[idx];
+        ulonglong2 r;
+        if (OP == 0) {
+            r.x = add_mod(x.x, y.x, pc.q);
+            r.y = add_mod(x.y, y.y, pc.q);
+        } else if (OP == 1) {
+            r.x = sub_mod(x.x, y.x, pc.q);
+            r.y = sub_mod(x.y, y.y, pc.q);
+        } else {
+            r.x = barrett_mul(x.x, y.x, pc);
+            r.y = barrett_mul(x.y, y.y, pc);
+        }
+        out[idx] = r;
+    }
+}
+
+__global__ void neg_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restrict__ out,
+                           const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total2) {
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 q = pp[(idx >> (logN - 1)) % L].pc.q;
+        const ulonglong2 x = a[idx];
+        ulonglong2 r;
+        r.x = neg_mod(x.x, q);
+        r.y = neg_mod(x.y, q);
+        out[idx] = r;
+    }
+}
+
+struct ScalarArgs {
+    tw_t s[TFB_MAX_L];
+};
+
+__global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restrict__ out,
+                                  const PrimeParams* __restrict__ pp, const ScalarArgs sa, const u32 L,
+                                  const u32 logN, const u64 total2) {
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 prime = (u32)((idx >> (logN - 1)) % L);
+        const u64 q = pp[prime].pc.q;
+        const tw_t s = sa.s[prime];
+        const ulonglong2 x = a[idx];
+        ulonglong2 r;
+        r.x = shoup_full(x.x, s.w, s.wp, q);
+        r.y = shoup_full(x.y, s.w, s.wp, q);
+        out[idx] = r;
+    }
+}
+
+static inline unsigned grid_for(u64 work, unsigned tb) {
+    u64 nb = (work + tb - 1) / tb;
+    const u64 cap = 148ull * 16;
+    return (unsigned)(nb < cap ? (nb ? nb : 1) : cap);
+}
+
+int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 rows, cudaStream_t st) {
+    if (!rows) return TFB_OK;
+    const u64 total2 = rows * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    if (op == 0) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<0><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    else if (op == 1) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<1><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    else { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<2><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_neg(tfb_ctx* c, const u64* a, u64* out, u64 rows, cudaStream_t st) {
+    if (!rows) return TFB_OK;
+    const u64 total2 = rows * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    { ProfScope ps(PC_ELEMENTWISE, st); neg_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_scalar_mul(tfb_ctx* c, const u64* a, const u64* s_host, u64* out, u64 rows, cudaStream_t st) {
+    if (!rows) return TFB_OK;
+    ScalarArgs sa;
+    for (u32 i = 0; i < c->L; i++) sa.s[i] = h_tw(s_host[i] % c->q[i], c->q[i]);
+    const u64 total2 = rows * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    { ProfScope ps(PC_ELEMENTWISE, st); scalar_mul_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (ulonglong2*)out, c->d_pp, sa, c->L, c->logN, total2); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ---------------------------------------------------- ciphertext tensor (dual)
+// a,b: [B][2][L][N] (NTT domain) -> out [B][3][L][N]: d0=a0 b0, d1=a0 b1+a1 b0, d2=a1 b1
+// (the coefficient-wise body of rlwe_she.jl:255-258 once everything is in dual form)
+__global__ void tensor_dual_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ b,
+                                   ulonglong2* __restrict__ out, const PrimeParams* __restrict__ pp, const u32 L,
+                                   const u32 logN, const u64 total2) {
+    const u64 rowlen = 1ull << (logN - 1);
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 n2 = idx & (rowlen - 1);
+        const u64 r = idx >> (logN - 1);  // (batch, prime)
+        const u64 bi = r / L, pi = r % L;
+        const PrimeConst pc = pp[pi].pc;
+        const u64 ia0 = ((bi * 2 + 0) * L + pi) * rowlen + n2, ia1 = ((bi * 2 + 1) * L + pi) * rowlen + n2;
+        const ulonglong2 a0 = a[ia0], a1 = a[ia1], b0 = b[ia0], b1 = b[ia1];
+        ulonglong2 d0, d1, d2;
+        d0.x = barrett_mul(a0.x, b0.x, pc);
+        d0.y = barrett_mul(a0.y, b0.y, pc);
+        d2.x = barrett_mul(a1.x, b1.x, pc);
+        d2.y = barrett_mul(a1.y, b1.y, pc);
+        acc128 s = {0, 0};
+        mac128(s, a0.x, b1.x);
+        mac128(s, a1.x, b0.x);
+        d1.x = red128_full(s, pc);
+        s.lo = s.hi = 0;
+        mac128(s, a0.y, b1.y);
+        mac128(s, a1.y, b0.y);
+        d1.y = red128_full(s, pc);
+        out[((bi * 3 + 0) * L + pi) * rowlen + n2] = d0;
+        out[((bi * 3 + 1) * L + pi) * rowlen + n2] = d1;
+        out[((bi * 3 + 2) * L + pi) * rowlen + n2] = d2;
+    }
+}
+
+int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 batch, cudaStream_t st) {
+    if (!batch) return TFB_OK;
+    const u64 total2 = batch * c->L * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    { ProfScope ps(PC_TENSOR, st); tensor_dual_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ------------------------------------------------------------------- Galois
+// out[(g i) mod N] = floor(g i / N) odd ? -in[i] : in[i]  (pow2_cyc_rings.jl:321-329),
+// evaluated as a gather: i = g^-1 r mod 2N; i < N ? in[i] : -in[i-N].
+__global__ void galois_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
+                              const u32 L, const u32 logN, const u32 ginv, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 row = idx >> logN;
+        const u32 r = (u32)(idx & (N - 1));
+        const u64 q = pp[row % L].pc.q;
+        const u32 i = (u32)(((u64)ginv * r) & (2 * N - 1));
+        const u64 v = in[(row << logN) + (i & (N - 1))];
+        out[idx] = i < N ? v : neg_mod(v, q);
+    }
+}
+
+int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStream_t st) {
+    if (!rows) return TFB_OK;
+    if (in == out) { tfb_set_error("tfb_galois cannot run in place"); return TFB_EINVAL; }
+    const u64 twoN = 2ull * c->N;
+    g %= twoN;
+    if ((g & 1) == 0) { tfb_set_error("galois element must be odd"); return TFB_EINVAL; }
+    // inverse of g modulo 2N (power of two): Newton iteration
+    u64 x = g;
+    for (int i = 0; i < 6; i++) x = x * (2 - g * x);
+    const u32 ginv = (u32)(x & (twoN - 1));
+    const u64 total = rows * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_LEVEL, st); galois_kernel<<<nb, tb, 0, st>>>(in, out, c->d_pp, c->L, c->logN, ginv, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ----------------------------------------------- rescale (modswitch, crt.jl:215-220)
+// in [P][L][N] -> out [P][L-1][N]: c'_i = (q_L mod q_i)^-1 (c_i - (c_L mod q_i)), c_L un-centred
+__global__ void rescale_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
+                               const ScalarArgs inv, const u32 L, const u32 logN, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (poly, i) with i < L-1
+        const u64 p = r / (L - 1);
+        const u32 i = (u32)(r % (L - 1));
+        const PrimeConst pc = pp[i].pc;
+        const u64 ci = in[((p * L + i) << logN) + n];
+        const u64 cl = barrett_red64(in[((p * L + (L - 1)) << logN) + n], pc);
+        out[idx] = shoup_full(sub_mod(ci, cl, pc.q), inv.s[i].w, inv.s[i].wp, pc.q);
+    }
+}
+
+int launch_rescale(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (c->L < 2) { tfb_set_error("rescale needs at least two primes"); return TFB_EINVAL; }
+    ScalarArgs sa;
+    const u64 qL = c->q[c->L - 1];
+    for (u32 i = 0; i + 1 < c->L; i++) {
+        if (qL % c->q[i] == 0) { tfb_set_error("rescale: primes not coprime"); return TFB_EINVAL; }
+        sa.s[i] = h_tw(h_invmod(qL % c->q[i], c->q[i]), c->q[i]);
+    }
+    const u64 total = polys * (c->L - 1) * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_LEVEL, st); rescale_kernel<<<nb, tb, 0, st>>>(in, out, c->d_pp, sa, c->L, c->logN, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// -------------------------------------------- CRTExpand (crt.jl:35-40): x P, append 0
+__global__ void crt_expand_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
+                                  const ScalarArgs pm, const u32 L, const u32 logN, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (poly, i) with i <= L
+        const u64 p = r / (L + 1);
+        const u32 i = (u32)(r % (L + 1));
+        u64 v = 0;
+        if (i < L) v = shoup_full(in[((p * L + i) << logN) + n], pm.s[i].w, pm.s[i].wp, pp[i].pc.q);
+        out[idx] = v;
+    }
+}
+
+int launch_crt_expand(tfb_ctx* c, u64 P, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    ScalarArgs sa;
+    for (u32 i = 0; i < c->L; i++) sa.s[i] = h_tw(P % c->q[i], c->q[i]);
+    const u64 total = polys * (c->L + 1) * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_LEVEL, st); crt_expand_kernel<<<nb, tb, 0, st>>>(in, out, c->d_pp, sa, c->L, c->logN, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ------------------------------------------------ Garner tables (per basis)
+// d_gm   [L][L] : gm[i][j]  = (prod_{k<j} q_k) mod q_i      (j < i)
+// d_ginv [L]    : Shoup pair of (prod_{k<i} q_k)^-1 mod q_i
+// d_halfmr [L]  : mixed-radix digits of floor(Q/2)
+struct GarnerTab {
+    const u64* gm;
+    const tw_t* ginv;
+    const u64* halfmr;
+};
+
+// mixed-radix digits of X given residues r[0..L)
+__device__ __forceinline__ void garner_digits(const u64* r, u64* d, const u32 L, const GarnerTab g,
+                                              const PrimeParams* __restrict__ pp) {
+    d[0] = r[0];
+    for (u32 i = 1; i < L; i++) {
+        const PrimeConst pc = pp[i].pc;
+        acc128 a = {0, 0};
+        for (u32 j = 0; j < i; j++) mac128(a, d[j], g.gm[i * L + j]);
+        const u64 s = red128_full(a, pc);
+        const tw_t iv = g.ginv[i];
+        d[i] = shoup_full(sub_mod(r[i], s, pc.q), iv.w, iv.wp, pc.q);
+    }
+}
+// X > floor(Q/2) ?
+__device__ __forceinline__ bool mr_above_half(const u64* d, const u32 L, const u64* __restrict__ half) {
+    for (int i = (int)L - 1; i >= 0; i--) {
+        const u64 h = half[i];
+        if (d[i] != h) return d[i] > h;
+    }
+    return false;
+}
+
+int build_garner(tfb_ctx* c) {
+    const u32 L = c->L;
+    std::vector<u64> gm((size_t)L * L, 0);
+    std::vector<tw_t> ginv(L);
+    for (u32 i = 0; i < L; i++) {
+        u64 M = 1 % c->q[i];
+        for (u32 j = 0; j < i; j++) {
+            gm[(size_t)i * L + j] = M;
+            if (c->q[j] % c->q[i] == 0) { tfb_set_error("RNS primes must be pairwise coprime"); return TFB_EINVAL; }
+            M = h_mulmod(M, c->q[j] % c->q[i], c->q[i]);
+        }
+        ginv[i] = h_tw(i ? h_invmod(M, c->q[i]) : 1 % c->q[i], c->q[i]);
+    }
+    // lazy 128-bit accumulation of L products d*m needs L * qmax^2 < 2^128
+    {
+        long double qm = 0;
+        for (u32 i = 0; i < L; i++) qm = c->q[i] > qm ? (long double)c->q[i] : qm;
+        c->conv_ok = (long double)L * qm * qm < 3.4e38L;
+    }
+    // digits of floor(Q/2): Q-1 has digits (q_i - 1); halve from the top
+    c->halfmr.assign(L, 0);
+    u64 carry = 0;
+    for (int i = (int)L - 1; i >= 0; i--) {
+        u128 cur = (u128)carry * c->q[i] + (c->q[i] - 1);
+        c->halfmr[i] = (u64)(cur / 2);
+        carry = (u64)(cur % 2);
+    }
+    // (Q-1)/2 == floor(Q/2) only for odd Q; for even Q (q_0 = 2) floor(Q/2) = Q/2 = (Q-1)/2 + carry-handling
+    bool even = false;
+    for (u32 i = 0; i < L; i++) even |= (c->q[i] % 2 == 0);
+    if (even) { tfb_set_error("even modulus not supported in RNS conversion"); return TFB_EUNSUPPORTED; }
+    u64* d_gm = nullptr;
+    TFB_CUDA(cudaMalloc(&d_gm, (size_t)L * L * sizeof(u64) + L * sizeof(u64)));
+    TFB_CUDA(cudaMemcpy(d_gm, gm.data(), (size_t)L * L * sizeof(u64), cudaMemcpyHostToDevice));
+    TFB_CUDA(cudaMemcpy(d_gm + (size_t)L * L, c->halfmr.data(), L * sizeof(u64), cudaMemcpyHostToDevice));
+    c->d_halfmr = d_gm;  // owns the allocation: [L*L] gm then [L] halfmr
+    TFB_CUDA(cudaMalloc(&c->d_ginv, L * sizeof(tw_t)));
+    TFB_CUDA(cudaMemcpy(c->d_ginv, ginv.data(), L * sizeof(tw_t), cudaMemcpyHostToDevice));
+    return TFB_OK;
+}
+static inline GarnerTab garner_of(const tfb_ctx* c) {
+    GarnerTab g;
+    g.gm = c->d_halfmr;
+    g.halfmr = c->d_halfmr + (size_t)c->L * c->L;
+    g.ginv = c->d_ginv;
+    return g;
+}
+
+// ---------------------------------------------- pair tables (from basis -> to basis)
+// ev   [Lt][Lf] : (prod_{k<i} qf_k) mod qt_j
+// qmod [Lt]     : Qf mod qt_j
+// hmod [Lt]     : floor(Qf/2) mod qt_j
+// qinv [Lt]     : Shoup pair of Qf^-1 mod qt_j (zero pair if not invertible)
+struct PairTab {
+    u64* ev;
+    u64* qmod;
+    u64* hmod;
+    tw_t* qinv;
+};
+struct PairKey {
+    const tfb_ctx* a;
+    const tfb_ctx* b;
+    bool operator<(const PairKey& o) const { return a < o.a || (a == o.a && b < o.b); }
+};
+static std::map<PairKey, PairTab> g_pairs;
+
+void tfb_forget_ctx_pairs(const tfb_ctx* c) {
+    for (auto it = g_pairs.begin(); it != g_pairs.end();) {
+        if (it->first.a == c || it->first.b == c) {
+            cudaFree(it->second.ev);
+            cudaFree(it->second.qinv);
+            it = g_pairs.erase(it);
+        } else
+            ++it;
+    }
+}
+
+static int get_pair(const tfb_ctx* from, const tfb_ctx* to, PairTab* out) {
+    PairKey k{from, to};
+    auto it = g_pairs.find(k);
+    if (it != g_pairs.end()) { *out = it->second; return TFB_OK; }
+    const u32 Lf = from->L, Lt = to->L;
+    std::vector<u64> buf((size_t)Lt * Lf + 2 * Lt);
+    std::vector<tw_t> qinv(Lt);
+    for (u32 j = 0; j < Lt; j++) {
+        const u64 m = to->q[j];
+        u64 M = 1 % m;
+        for (u32 i = 0; i < Lf; i++) {
+            buf[(size_t)j * Lf + i] = M;
+            M = h_mulmod(M, from->q[i] % m, m);
+        }
+        buf[(size_t)Lt * Lf + j] = M;  // Qf mod m
+        // floor(Qf/2) mod m by Horner over its mixed-radix digits
+        u64 h = 0;
+        for (int i = (int)Lf - 1; i >= 0; i--) h = (u64)(((u128)h * (from->q[i] % m) + from->halfmr[i] % m) % m);
+        buf[(size_t)Lt * Lf + Lt + j] = h;
+        tw_t z;
+        z.w = z.wp = 0;
+        qinv[j] = M ? h_tw(h_invmod(M, m), m) : z;
+    }
+    PairTab t;
+    TFB_CUDA(cudaMalloc(&t.ev, buf.size() * sizeof(u64)));
+    TFB_CUDA(cudaMemcpy(t.ev, buf.data(), buf.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    t.qmod = t.ev + (size_t)Lt * Lf;
+    t.hmod = t.qmod + Lt;
+    TFB_CUDA(cudaMalloc(&t.qinv, Lt * sizeof(tw_t)));
+    TFB_CUDA(cudaMemcpy(t.qinv, qinv.data(), Lt * sizeof(tw_t), cudaMemcpyHostToDevice));
+    g_pairs[k] = t;
+    *out = t;
+    return TFB_OK;
+}
+
+// residue of the mixed-radix number d (basis "from") modulo target prime j
+__device__ __forceinline__ u64 mr_eval(const u64* d, const u32 Lf, const u64* __restrict__ ev_row,
+                                       const PrimeConst& pc) {
+    acc128 a = {0, 0};
+    for (u32 i = 0; i < Lf; i++) mac128(a, d[i], ev_row[i]);
+    return red128_full(a, pc);
+}
+
+// ------------------------------------ switch / switchel (bfv.jl:202-226)
+// in [P][Lf][N] -> out [P][Lt][N]: centred lift from Qf (strict '>' Qf>>1), reduce into target basis
+__global__ void base_switch_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 Lf, const u32 Lt,
+                                   const u32 logN, const GarnerTab g, const PrimeParams* __restrict__ ppf,
+                                   const PrimeParams* __restrict__ ppt, const PairTab pt, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 r[MAXD], d[MAXD];
+    for (u32 i = 0; i < Lf; i++) r[i] = in[((p * Lf + i) << logN) + n];
+    garner_digits(r, d, Lf, g, ppf);
+    const bool neg = mr_above_half(d, Lf, g.halfmr);
+    for (u32 j = 0; j < Lt; j++) {
+        const PrimeConst pc = ppt[j].pc;
+        u64 v = mr_eval(d, Lf, pt.ev + (size_t)j * Lf, pc);
+        if (neg) v = sub_mod(v, pt.qmod[j], pc.q);
+        out[((p * Lt + j) << logN) + n] = v;
+    }
+}
+
+int launch_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (from->N != to->N) { tfb_set_error("base switch: ring degrees differ"); return TFB_EINVAL; }
+    if (from->L > MAXD || !from->conv_ok) { tfb_set_error("base switch: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    PairTab pt;
+    int rc = get_pair(from, to, &pt);
+    if (rc) return rc;
+    const u64 total = polys * from->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_BASE_SWITCH, st); base_switch_kernel<<<(unsigned)nb, tb, 0, st>>>(in, out, from->L, to->L, from->logN, garner_of(from), from->d_pp, to->d_pp, pt, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ------------------------- mul_contract (bfv.jl:35-40, 172-190): y = rha(t x, Q) mod q_i
+// in [P][Lb][N] over the big basis (x centred in Q_big), out [P][L][N].
+// Exact, all in word arithmetic:  |x| = X or Qb - X;  a = t|x| + (Q-1)/2;  R = a mod Q
+// (known through its residues a mod q_i);  y_abs = (a - R)/Q computed modulo every
+// p_j, converted back to the q_i basis;  sign restored at the end.  For odd Q,
+// floor((t|x| + (Q-1)/2)/Q) is exactly round-half-away (div_hacks.jl:120-135).
+struct ContractArgs {
+    tw_t t_q[MAXD];  // t mod q_i
+    tw_t t_b[MAXD];  // t mod p_j
+};
+__global__ void bfv_contract_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 L, const u32 Lb,
+                                    const u32 logN, const GarnerTab gq, const GarnerTab gb,
+                                    const PrimeParams* __restrict__ ppq, const PrimeParams* __restrict__ ppb,
+                                    const PairTab b2q, const PairTab q2b, const u64* __restrict__ hq,
+                                    const ContractArgs ca, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 rb[MAXD], db[MAXD], aq[MAXD], dq[MAXD];
+    for (u32 j = 0; j < Lb; j++) rb[j] = in[((p * Lb + j) << logN) + n];
+    garner_digits(rb, db, Lb, gb, ppb);
+    const bool neg = mr_above_half(db, Lb, gb.halfmr);
+    // a mod q_i = t |x| + h
+    for (u32 i = 0; i < L; i++) {
+        const PrimeConst pc = ppq[i].pc;
+        u64 v = mr_eval(db, Lb, b2q.ev + (size_t)i * Lb, pc);  // X mod q_i
+        if (neg) v = sub_mod(b2q.qmod[i], v, pc.q);             // (Qb - X) mod q_i
+        v = shoup_full(v, ca.t_q[i].w, ca.t_q[i].wp, pc.q);
+        aq[i] = add_mod(v, hq[i], pc.q);
+    }
+    // R = a mod Q, mixed radix over the q basis
+    garner_digits(aq, dq, L, gq, ppq);
+    // y_abs mod p_j = (t|x| + h - R) Q^-1
+    for (u32 j = 0; j < Lb; j++) {
+        const PrimeConst pc = ppb[j].pc;
+        const u64 xa = neg ? neg_mod(rb[j], pc.q) : rb[j];
+        const u64 a = add_mod(shoup_full(xa, ca.t_b[j].w, ca.t_b[j].wp, pc.q), q2b.hmod[j], pc.q);
+        const u64 Rj = mr_eval(dq, L, q2b.ev + (size_t)j * L, pc);
+        rb[j] = shoup_full(sub_mod(a, Rj, pc.q), q2b.qinv[j].w, q2b.qinv[j].wp, pc.q);
+    }
+    // y_abs back to the q basis (y_abs < Q_big because t < Q)
+    garner_digits(rb, db, Lb, gb, ppb);
+    for (u32 i = 0; i < L; i++) {
+        const PrimeConst pc = ppq[i].pc;
+        const u64 v = mr_eval(db, Lb, b2q.ev + (size_t)i * Lb, pc);
+        out[((p * L + i) << logN) + n] = neg ? neg_mod(v, pc.q) : v;
+    }
+}
+
+int launch_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (cq->N != cb->N) { tfb_set_error("bfv contract: ring degrees differ"); return TFB_EINVAL; }
+    if (cq->L > MAXD || cb->L > MAXD || !cq->conv_ok || !cb->conv_ok) { tfb_set_error("bfv contract: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    for (u32 i = 0; i < cq->L; i++)
+        for (u32 j = 0; j < cb->L; j++)
+            if (cq->q[i] == cb->q[j]) { tfb_set_error("bfv contract: the two bases must be disjoint"); return TFB_EINVAL; }
+    PairTab b2q, q2b, q2q;
+    int rc = get_pair(cb, cq, &b2q);
+    if (rc) return rc;
+    if ((rc = get_pair(cq, cb, &q2b))) return rc;
+    if ((rc = get_pair(cq, cq, &q2q))) return rc;
+    ContractArgs ca;
+    for (u32 i = 0; i < cq->L; i++) ca.t_q[i] = h_tw(t % cq->q[i], cq->q[i]);
+    for (u32 j = 0; j < cb->L; j++) ca.t_b[j] = h_tw(t % cb->q[j], cb->q[j]);
+    const u64 total = polys * cq->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_BFV_CONTRACT, st); bfv_contract_kernel<<<(unsigned)nb, tb, 0, st>>>(in, out, cq->L, cb->L, cq->logN, garner_of(cq), garner_of(cb),
+                                                     cq->d_pp, cb->d_pp, b2q, q2b, q2q.hmod, ca, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ---------------------------------------- keyswitch digit polys (rlwe_she.jl:326-338)
+// cend: last component of each ciphertext, rows [B][stride_polys][L][N] starting at the
+// component (the caller passes the pointer to component comps-1 and the per-ciphertext
+// stride in words).  out [B][Dn][Lt][N] holds digits k0 .. k0+Dn-1.
+// w == 0: CRT digits -- digit i = centred residue i re-embedded in every target prime (:329)
+__global__ void ks_digits_crt_kernel(const u64* __restrict__ cend, const u64 ct_stride, u64* __restrict__ out,
+                                     const u32 L, const u32 Lt, const u32 logN, const u32 k0, const u32 Dn,
+                                     const PrimeParams* __restrict__ ppq, const PrimeParams* __restrict__ ppt,
+                                     const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (b, kk)
+        const u64 b = r / Dn;
+        const u32 i = k0 + (u32)(r % Dn);
+        const u64 qi = ppq[i].pc.q;
+        const u64 c = cend[b * ct_stride + ((u64)i << logN) + n];
+        const bool neg = c > (qi >> 1);
+        const u64 mag = neg ? qi - c : c;
+        for (u32 j = 0; j < Lt; j++) {
+            const PrimeConst pc = ppt[j].pc;
+            u64 v = barrett_red64(mag, pc);
+            out[((r * Lt + j) << logN) + n] = neg ? neg_mod(v, pc.q) : v;
+        }
+    }
+}
+// w > 0: base-2^w digits of the un-centred integer X in [0,Q) (:331-337)
+__global__ void ks_digits_pow2_kernel(const u64* __restrict__ cend, const u64 ct_stride, u64* __restrict__ out,
+                                      const u32 L, const u32 Lt, const u32 logN, const u32 w, const u32 k0,
+                                      const u32 Dn, const GarnerTab g, const PrimeParams* __restrict__ ppq,
+                                      const PrimeParams* __restrict__ ppt, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 b = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 r[MAXD], d[MAXD], X[MAXD + 1];
+    for (u32 i = 0; i < L; i++) r[i] = cend[b * ct_stride + ((u64)i << logN) + n];
+    garner_digits(r, d, L, g, ppq);
+    // binary limbs by Horner: X = (..(d_{L-1} q_{L-2} + d_{L-2}) q_{L-3} + ..) q_0 + d_0
+    u32 nl = 1;
+    X[0] = d[L - 1];
+    for (int i = (int)L - 2; i >= 0; i--) {
+        const u64 m = ppq[i].pc.q;
+        u64 carry = d[i];
+        for (u32 k = 0; k < nl; k++) {
+            const u64 lo = X[k] * m, hi = __umul64hi(X[k], m);
+            const u64 s = lo + carry;
+            X[k] = s;
+            carry = hi + (s < lo);
+        }
+        X[nl++] = carry;
+    }
+    const u64 mask = w >= 64 ? ~0ull : ((1ull << w) - 1);
+    for (u32 kk = 0; kk < Dn; kk++) {
+        const u32 bit = (k0 + kk) * w, limb = bit >> 6, off = bit & 63;
+        u64 v = limb < nl ? X[limb] >> off : 0;
+        if (off + w > 64 && limb + 1 < nl) v |= X[limb + 1] << (64 - off);
+        v &= mask;
+        for (u32 j = 0; j < Lt; j++) {
+            const PrimeConst pc = ppt[j].pc;
+            out[(((b * Dn + kk) * Lt + j) << logN) + n] = v < pc.q ? v : barrett_red64(v, pc);
+        }
+    }
+}
+
+int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct_stride, u64* out, u32 k0, u32 Dn,
+                     u64 batch, cudaStream_t st) {
+    if (!batch || !Dn) return TFB_OK;
+    if (c->N != target->N) { tfb_set_error("keyswitch digits: ring degrees differ"); return TFB_EINVAL; }
+    if (w < 0 || w > 63) { tfb_set_error("keyswitch digits: relin_window must be in 0..63"); return TFB_EINVAL; }
+    if (w == 0) {
+        if (k0 + Dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
+        const u64 total = batch * Dn * c->N;
+        const unsigned tb = 256, nb = grid_for(total, tb);
+        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_crt_kernel<<<nb, tb, 0, st>>>(cend, ct_stride, out, c->L, target->L, c->logN, k0, Dn, c->d_pp, target->d_pp, total); }
+    } else {
+        if (c->L > MAXD || !c->conv_ok) { tfb_set_error("keyswitch digits: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+        const u64 total = batch * c->N;
+        const unsigned tb = 128;
+        const u64 nb = (total + tb - 1) / tb;
+        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_pow2_kernel<<<(unsigned)nb, tb, 0, st>>>(cend, ct_stride, out, c->L, target->L, c->logN, (u32)w, k0, Dn,
+                                                          garner_of(c), c->d_pp, target->d_pp, total); }
+    }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// --------------------- key accumulation in the NTT domain (rlwe_she.jl:340-344)
+// acc [B][2][L][N] (dual): acc[b][0] (+)= sum_k masked_k . p_k ; acc[b][1] (+)= sum_k mask_k . p_k
+// dig [B][Dn][L][N] dual; key [D][2][L][N] dual, component 0 = mask, 1 = masked; uses
+// key digits k0 .. k0+Dn-1.
+__global__ void ks_accum_kernel(const u64* __restrict__ dig, const u64* __restrict__ key, u64* __restrict__ acc,
+                                const u32 L, const u32 logN, const u32 k0, const u32 Dn, const int accumulate,
+                                const PrimeParams* __restrict__ pp, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (b, i)
+        const u64 b = r / L;
+        const u32 i = (u32)(r % L);
+        const PrimeConst pc = pp[i].pc;
+        acc128 a1 = {0, 0}, a2 = {0, 0};
+        u64* o1 = acc + (((b * 2 + 0) * L + i) << logN) + n;
+        u64* o2 = acc + (((b * 2 + 1) * L + i) << logN) + n;
+        if (accumulate) {
+            a1.lo = *o1;
+            a2.lo = *o2;
+        }
+        for (u32 kk = 0; kk < Dn; kk++) {
+            const u64 p = dig[(((b * Dn + kk) * L + i) << logN) + n];
+            const u64 km = key[((((u64)(k0 + kk) * 2 + 0) * L + i) << logN) + n];
+            const u64 kd = key[((((u64)(k0 + kk) * 2 + 1) * L + i) << logN) + n];
+            mac128(a1, kd, p);
+            mac128(a2, km, p);
+            if ((kk & 7) == 7) {
+                a1.lo = red128_full(a1, pc);
+                a1.hi = 0;
+                a2.lo = red128_full(a2, pc);
+                a2.hi = 0;
+            }
+        }
+        *o1 = red128_full(a1, pc);
+        *o2 = red128_full(a2, pc);
+    }
+}
+
+int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
+                    cudaStream_t st) {
+    if (!batch) return TFB_OK;
+    const u64 total = batch * c->L * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_KS_ACCUM, st); ks_accum_kernel<<<nb, tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// ---------------- keyswitch epilogue: add the switched part onto (c1, c2)
+// plain params:      out[b][k] = (k < comps-1 ? ct[b][k] : 0) + acc[b][k]            (rlwe_she.jl:323-324,343-346)
+// ModulusRaised:     v = P * ct[b][k] (+0 on the special row) + acc_ext[b][k];  out = modswitch(v)
+//                    (modulusraising.jl:35-42 with crt.jl:215-220)
+__global__ void ks_finish_kernel(const u64* __restrict__ ct, const u32 comps, const u64* __restrict__ acc,
+                                 u64* __restrict__ out, const u32 L, const u32 logN,
+                                 const PrimeParams* __restrict__ pp, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (b, k, i)
+        const u32 i = (u32)(r % L);
+        const u64 bk = r / L;
+        const u32 k = (u32)(bk & 1);
+        const u64 b = bk >> 1;
+        const u64 q = pp[i].pc.q;
+        u64 v = acc[idx];
+        if (k + 1 < comps) v = add_mod(v, ct[(((b * comps + k) * L + i) << logN) + n], q);
+        out[idx] = v;
+    }
+}
+struct RaiseArgs {
+    tw_t pm[TFB_MAX_L];   // P mod q_i
+    tw_t inv[TFB_MAX_L];  // (P mod q_i)^-1
+};
+__global__ void ks_finish_raised_kernel(const u64* __restrict__ ct, const u32 comps, const u64* __restrict__ acc,
+                                        u64* __restrict__ out, const u32 l, const u32 logN,
+                                        const PrimeParams* __restrict__ pp, const RaiseArgs ra, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (b, k, i) with i < l
+        const u32 i = (u32)(r % l);
+        const u64 bk = r / l;
+        const u32 k = (u32)(bk & 1);
+        const u64 b = bk >> 1;
+        const PrimeConst pc = pp[i].pc;
+        u64 v = acc[((bk * (l + 1) + i) << logN) + n];
+        if (k + 1 < comps)
+            v = add_mod(v, shoup_full(ct[(((b * comps + k) * l + i) << logN) + n], ra.pm[i].w, ra.pm[i].wp, pc.q), pc.q);
+        const u64 sp = barrett_red64(acc[((bk * (l + 1) + l) << logN) + n], pc);  // special-prime row, un-centred
+        out[idx] = shoup_full(sub_mod(v, sp, pc.q), ra.inv[i].w, ra.inv[i].wp, pc.q);
+    }
+}
+
+int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st) {
+    if (!batch) return TFB_OK;
+    const u64 total = batch * 2 * c->L * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_KS_FINISH, st); ks_finish_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, out, c->L, c->logN, c->d_pp, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch,
+                            cudaStream_t st) {
+    if (!batch) return TFB_OK;
+    const u64 P = ext->q[ext->L - 1];
+    RaiseArgs ra;
+    for (u32 i = 0; i < c->L; i++) {
+        if (P % c->q[i] == 0) { tfb_set_error("special prime must differ from the ciphertext primes"); return TFB_EINVAL; }
+        ra.pm[i] = h_tw(P % c->q[i], c->q[i]);
+        ra.inv[i] = h_tw(h_invmod(P % c->q[i], c->q[i]), c->q[i]);
+    }
+    const u64 total = batch * 2 * c->L * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_KS_FINISH, st); ks_finish_raised_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, out, c->L, c->logN, c->d_pp, ra, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}

@@ -1,0 +1,296 @@
+"""ctypes binding of libtoyfhe_b200.so -- the Python stand-in for the Julia
+``ccall`` shim (julia/ToyFHEB200.jl).  Torch is used only for
+device memory and streams; every operation is one call through the C-ABI.
+
+There is no CPU fallback: if the library is missing or a CUDA call fails the
+binding raises (``EngineError``)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtoyfhe_b200.so")
+
+_u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+# every symbol include/toyfhe_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tfb_last_error", "tfb_version", "tfb_kernel_launches",
+    "tfb_profile_enable", "tfb_profile_classes", "tfb_profile_class_name", "tfb_profile_read",
+    "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
+    "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
+    "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
+    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
+    "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
+    "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
+    "tfb_keyswitch_digits", "tfb_keyswitch",
+    "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
+    "tfb_bfv_mul_host", "tfb_rescale_host",
+]
+
+
+class EngineError(RuntimeError):
+    """Raised for any non-zero return code of the C-ABI (the Julia shim throws
+    the same way where the reference would raise / @assert)."""
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.tfb_last_error.restype = C.c_char_p
+        lib.tfb_kernel_launches.restype = C.c_ulonglong
+        lib.tfb_ctx_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32, _u64p, _u64p, C.POINTER(C.c_void_p)]
+        lib.tfb_ctx_destroy.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EngineError(f"toyfhe_b200 error {rc}: {load_library().tfb_last_error().decode()}")
+
+
+def kernel_launches() -> int:
+    return int(load_library().tfb_kernel_launches())
+
+
+def profile_enable(on: bool) -> None:
+    _check(load_library().tfb_profile_enable(C.c_int(1 if on else 0)))
+
+
+def profile_read(reset: bool = True) -> dict:
+    """per-kernel-class {name: (launches, total_ms)} measured with CUDA events"""
+    lib = load_library()
+    n = lib.tfb_profile_classes()
+    counts = (C.c_ulonglong * n)()
+    ms = (C.c_double * n)()
+    _check(lib.tfb_profile_read(counts, ms, C.c_int(1 if reset else 0)))
+    lib.tfb_profile_class_name.restype = C.c_char_p
+    return {lib.tfb_profile_class_name(i).decode(): (int(counts[i]), float(ms[i])) for i in range(n)}
+
+
+# ---- host-only helpers (no GPU needed) -------------------------------------
+def prime_chain(N: int, logqs: Sequence[int]):
+    """NegacyclicRing(N, logqs) prime chain + minimal roots (crt.jl:282-295)."""
+    lib = load_library()
+    n = len(logqs)
+    lq = (C.c_int32 * n)(*[int(x) for x in logqs])
+    q = (C.c_uint64 * n)()
+    psi = (C.c_uint64 * n)()
+    _check(lib.tfb_prime_chain(C.c_uint32(N), lq, C.c_uint32(n), q, psi))
+    return [int(x) for x in q], [int(x) for x in psi]
+
+
+def minimal_primitive_root(q: int, n: int) -> int:
+    out = C.c_uint64()
+    _check(load_library().tfb_minimal_primitive_root(C.c_uint64(q), C.c_uint64(n), C.byref(out)))
+    return int(out.value)
+
+
+def ndigits(qs: Sequence[int], w: int) -> int:
+    arr = (C.c_uint64 * len(qs))(*[int(x) for x in qs])
+    out = C.c_uint32()
+    _check(load_library().tfb_ndigits(arr, C.c_uint32(len(qs)), C.c_uint32(w), C.byref(out)))
+    return int(out.value)
+
+
+# ---- device context ----------------------------------------------------------
+def _ptr(t) -> C.c_void_p:
+    """device (torch tensor) or host (numpy / pinned torch tensor) buffer -> pointer"""
+    if isinstance(t, np.ndarray):
+        assert t.dtype == np.uint64 and t.flags["C_CONTIGUOUS"]
+        return C.c_void_p(t.ctypes.data)
+    assert t.is_contiguous() and t.element_size() == 8, "need a contiguous 64-bit tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream) -> C.c_void_p:
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class Context:
+    """One NegacyclicRing{CRTEncoded{L}, N}(psi) resident on a GPU
+    (pow2_cyc_rings.jl:27-47; crt.jl:282-295)."""
+
+    def __init__(self, N: int, qs: Sequence[int], psis: Sequence[int], device: Optional[int] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise EngineError("no CUDA device: the engine has no CPU fallback")
+        lib = load_library()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.N, self.L = int(N), len(qs)
+        self.qs, self.psis = [int(q) for q in qs], [int(p) for p in psis]
+        q = (C.c_uint64 * self.L)(*self.qs)
+        psi = (C.c_uint64 * self.L)(*self.psis)
+        h = C.c_void_p()
+        _check(lib.tfb_ctx_create(C.c_int(self.device), C.c_uint32(self.N), C.c_uint32(self.L), q, psi, C.byref(h)))
+        self.h = h
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.tfb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- allocation helpers (torch owns the memory)
+    def empty(self, *shape):
+        import torch
+        return torch.empty(*shape, dtype=torch.int64, device=f"cuda:{self.device}")
+
+    def to_device(self, a: np.ndarray):
+        import torch
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        return torch.from_numpy(a.view(np.int64)).to(f"cuda:{self.device}")
+
+    @staticmethod
+    def to_host(t) -> np.ndarray:
+        return t.detach().cpu().numpy().view(np.uint64)
+
+    def _rows(self, t) -> int:
+        n = t.numel() if hasattr(t, "numel") else t.size
+        assert n % (self.N * self.L) == 0, "buffer must hold whole RNS polynomials [..][L][N]"
+        return n // self.N
+
+    def _polys(self, t) -> int:
+        return self._rows(t) // self.L
+
+    # -- transforms
+    def ntt_fwd(self, a, out=None, stream=None):
+        out = self.empty(a.shape) if out is None else out
+        _check(self._lib.tfb_ntt_fwd(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def ntt_inv(self, a, out=None, stream=None):
+        out = self.empty(a.shape) if out is None else out
+        _check(self._lib.tfb_ntt_inv(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def _bin(self, fn, a, b, out, stream):
+        assert a.shape == b.shape
+        out = self.empty(a.shape) if out is None else out
+        _check(fn(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def add(self, a, b, out=None, stream=None): return self._bin(self._lib.tfb_add, a, b, out, stream)
+    def sub(self, a, b, out=None, stream=None): return self._bin(self._lib.tfb_sub, a, b, out, stream)
+    def mul(self, a, b, out=None, stream=None): return self._bin(self._lib.tfb_mul, a, b, out, stream)
+    def ring_mul(self, a, b, out=None, stream=None): return self._bin(self._lib.tfb_ring_mul, a, b, out, stream)
+
+    def neg(self, a, out=None, stream=None):
+        out = self.empty(a.shape) if out is None else out
+        _check(self._lib.tfb_neg(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def scalar_mul(self, a, s: int, out=None, stream=None):
+        out = self.empty(a.shape) if out is None else out
+        sr = (C.c_uint64 * self.L)(*[int(s) % q for q in self.qs])
+        _check(self._lib.tfb_scalar_mul(self.h, _ptr(a), sr, _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def galois(self, a, g: int, out=None, stream=None):
+        out = self.empty(a.shape) if out is None else out
+        _check(self._lib.tfb_galois(self.h, C.c_uint64(int(g)), _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    # -- level changes
+    def rescale(self, a, out=None, stream=None):
+        out = self.empty(tuple(a.shape[:-2]) + (self.L - 1, self.N)) if out is None else out
+        _check(self._lib.tfb_rescale(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        return out
+
+    def crt_expand(self, a, P: int, out=None, stream=None):
+        out = self.empty(tuple(a.shape[:-2]) + (self.L + 1, self.N)) if out is None else out
+        _check(self._lib.tfb_crt_expand(self.h, C.c_uint64(int(P)), _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        return out
+
+    # -- ciphertext multiply
+    def _batch(self, c, comps):
+        n = c.numel() if hasattr(c, "numel") else c.size
+        assert n % (comps * self.L * self.N) == 0
+        return n // (comps * self.L * self.N)
+
+    def ct_tensor(self, c1, c2, out=None, stream=None):
+        B = self._batch(c1, 2)
+        out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
+        _check(self._lib.tfb_ct_tensor(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    def bfv_switch(self, to: "Context", a, out=None, stream=None):
+        out = to.empty(tuple(a.shape[:-2]) + (to.L, to.N)) if out is None else out
+        _check(self._lib.tfb_bfv_switch(self.h, to.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        return out
+
+    def bfv_contract(self, big: "Context", t: int, a, out=None, stream=None):
+        out = self.empty(tuple(a.shape[:-2]) + (self.L, self.N)) if out is None else out
+        _check(self._lib.tfb_bfv_contract(self.h, big.h, C.c_uint64(int(t)), _ptr(a), _ptr(out), C.c_uint64(big._polys(a)), _stream_ptr(stream)))
+        return out
+
+    def bfv_mul(self, big: "Context", t: int, c1, c2, out=None, stream=None):
+        B = self._batch(c1, 2)
+        out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
+        _check(self._lib.tfb_bfv_mul(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    # -- key switching
+    def keyswitch_digits(self, cend, w: int, target: Optional["Context"] = None, out=None, stream=None):
+        target = self if target is None else target
+        D = self.L if w == 0 else ndigits(self.qs, w)
+        B = self._polys(cend)
+        out = self.empty(tuple(cend.shape[:-2]) + (D, target.L, self.N)) if out is None else out
+        _check(self._lib.tfb_keyswitch_digits(self.h, target.h, C.c_uint32(w), _ptr(cend), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    def keyswitch(self, key_dual, ct, w: int, ext: Optional["Context"] = None, out=None, stream=None):
+        """ct [B][comps][L][N] primal, key_dual [D][2][L'][N] (NTT domain)."""
+        comps = ct.shape[-3]
+        B = self._batch(ct, comps)
+        D = key_dual.shape[0]
+        out = self.empty(tuple(ct.shape[:-3]) + (2, self.L, self.N)) if out is None else out
+        _check(self._lib.tfb_keyswitch(self.h, ext.h if ext is not None else None, C.c_uint32(w), _ptr(key_dual),
+                                       C.c_uint32(D), _ptr(ct), C.c_uint32(comps), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    # -- host-buffer entry points (numpy uint64 or pinned torch tensors)
+    def ntt_fwd_host(self, a, out, stream=None):
+        _check(self._lib.tfb_ntt_fwd_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def ntt_inv_host(self, a, out, stream=None):
+        _check(self._lib.tfb_ntt_inv_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def ring_mul_host(self, a, b, out, stream=None):
+        _check(self._lib.tfb_ring_mul_host(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        return out
+
+    def ct_tensor_host(self, c1, c2, out, stream=None):
+        _check(self._lib.tfb_ct_tensor_host(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream)))
+        return out
+
+    def bfv_mul_host(self, big: "Context", t: int, c1, c2, out, stream=None):
+        _check(self._lib.tfb_bfv_mul_host(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out),
+                                          C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream)))
+        return out
+
+    def rescale_host(self, a, out, stream=None):
+        _check(self._lib.tfb_rescale_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        return out
