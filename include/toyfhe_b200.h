@@ -55,6 +55,14 @@ int tfb_profile_enable(int on);
 int tfb_profile_classes(void);
 const char* tfb_profile_class_name(int cls);
 int tfb_profile_read(unsigned long long* counts, double* total_ms, int reset);
+/* testing hook: route base conversions through the generic runtime-L kernels even
+ * where a register-resident specialisation exists (both must agree bit for bit) */
+int tfb_debug_force_generic(int on);
+/* kernel selection hook: 1 (default) = 512x32 row kernels, 2 = persistent TMA-prefetched 1024x16 kernels for N >= 2^14 */
+int tfb_debug_ntt_version(int v);
+/* testing hook: force the Harvey (conditional subtract per level) forward ladder even when every prime
+ * qualifies for the lazy ladder */
+int tfb_debug_ntt_force_harvey(int on);
 
 /* ---- ring construction helpers (host only, no GPU needed) ---------------- */
 /* NegacyclicRing(N, logqs) prime chain, crt.jl:282-295: ascending-logq order,

@@ -7,10 +7,14 @@
 #include <vector>
 
 #include "../../toyfhe.jl_b200/csrc/ntt_core.cuh"
+#include "../../toyfhe.jl_b200/csrc/ntt_core2.cuh"
 #include "../../toyfhe.jl_b200/csrc/tables.h"
 
-template <int R>
+static u32 log2floor(u64 q) { return 63 - (u32)__builtin_clzll(q); }
+
+template <int R, int MODE>
 static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+    const RedParams rp = make_red(q, log2floor(q));
     typedef NttGeo<R> Geo;
     const u64 Nrow = (u64)Geo::N << s0;
     HostTables ht;
@@ -18,9 +22,9 @@ static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
     std::vector<u64> smem(Geo::N), regs((size_t)Geo::T * 32);
     for (u32 blk = 0; blk < (1u << s0); blk++) {
         if (!inverse) {
-            for (u32 t = 0; t < Geo::T; t++) fwd_phaseA<R>(&regs[t * 32], in + (u64)blk * Geo::N, smem.data(), ht.fwd.data(), q, t, s0, blk);
-            for (u32 t = 0; t < Geo::T; t++) fwd_phaseB<R>(&regs[t * 32], smem.data(), ht.fwd.data(), q, t, s0, blk);
-            for (u32 t = 0; t < Geo::T; t++) fwd_phaseC<R>(&regs[t * 32], out, smem.data(), ht.fwd.data(), q, t, s0, blk);
+            for (u32 t = 0; t < Geo::T; t++) fwd_phaseA<R, MODE>(&regs[t * 32], in + (u64)blk * Geo::N, smem.data(), ht.fwd.data(), rp, t, s0, blk);
+            for (u32 t = 0; t < Geo::T; t++) fwd_phaseB<R, MODE>(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
+            for (u32 t = 0; t < Geo::T; t++) fwd_phaseC<R, MODE>(&regs[t * 32], out, smem.data(), ht.fwd.data(), rp, t, s0, blk);
         } else {
             for (u32 t = 0; t < Geo::T; t++) inv_phaseC<R>(&regs[t * 32], in, smem.data(), ht.inv.data(), q, t, s0, blk);
             for (u32 t = 0; t < Geo::T; t++) inv_phaseB<R>(&regs[t * 32], smem.data(), ht.inv.data(), q, t, s0, blk);
@@ -32,15 +36,13 @@ static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
 // emulates the fast kernel on one row of length 2^(10+R+s0).  For s0>0 only the
 // row-resident part is emulated: forward expects stages 1..s0 already applied to
 // `in`; inverse leaves stages s0..1 (and the N^-1 scale) to the caller.
-extern "C" int emu_ntt(int R, int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+extern "C" int emu_ntt(int R, int mode, int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+#define RUN(RR) case RR: if (mode) run<RR, 1>(inverse, q, psi, s0, in, out); else run<RR, 0>(inverse, q, psi, s0, in, out); break;
     switch (R) {
-        case 0: run<0>(inverse, q, psi, s0, in, out); break;
-        case 1: run<1>(inverse, q, psi, s0, in, out); break;
-        case 2: run<2>(inverse, q, psi, s0, in, out); break;
-        case 3: run<3>(inverse, q, psi, s0, in, out); break;
-        case 4: run<4>(inverse, q, psi, s0, in, out); break;
+        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
         default: return 1;
     }
+#undef RUN
     return 0;
 }
 
@@ -84,4 +86,81 @@ extern "C" int emu_bank_conflicts(int R) {
         case 4: return conflicts<4>();
     }
     return -1;
+}
+
+// ---- second-generation kernel (1024 threads x 16 residues, N = 2^14 sub-blocks)
+// Execution order mirrors the CUDA kernel's synchronisation: middle passes run warp
+// by warp (all 32 lanes load, then all 32 lanes store: only __syncwarp between),
+// __syncthreads between passes.  A cross-warp hazard would show up as a mismatch.
+template <int MODE>
+static int run2(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out);
+extern "C" int emu_ntt2(int mode, int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+    return mode ? run2<1>(inverse, q, psi, s0, in, out) : run2<0>(inverse, q, psi, s0, in, out);
+}
+template <int MODE>
+static int run2(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+    using namespace v2;
+    const RedParams rp = make_red(q, log2floor(q));
+    const u64 Nrow = (u64)N << s0;
+    HostTables ht;
+    build_tables(Nrow, q, psi, ht);
+    std::vector<u64> smem(N), regs((size_t)T * 16);
+    for (u32 blk = 0; blk < (1u << s0); blk++) {
+        if (!inverse) {
+            memcpy(smem.data(), in + (u64)blk * N, N * sizeof(u64));  // what the TMA bulk copy delivers
+            for (int k = 0; k < 3; k++)
+                for (u32 w = 0; w < T / 32; w++) {
+                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); fwd_mid_load(&regs[t * 16], smem.data(), c); }
+                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); fwd_mid_compute<MODE>(&regs[t * 16], ht.fwd.data(), c, rp); fwd_mid_store(&regs[t * 16], smem.data(), c); }
+                }
+            for (u32 t = 0; t < T; t++) fwd_last_load(&regs[t * 16], smem.data(), t);
+            for (u32 t = 0; t < T; t++) fwd_last_compute_store<MODE>(&regs[t * 16], out, ht.fwd.data(), rp, t, s0, blk);
+        } else {
+            // s0 == 0: the row is first copied flat into shared memory; s0 > 0: gathered from global
+            const u64* src = in;
+            std::vector<u64> flat;
+            if (s0 == 0) { flat.assign(in, in + N); src = flat.data(); }
+            for (u32 t = 0; t < T; t++) inv_first_load(&regs[t * 16], src, t, s0, blk);
+            for (u32 t = 0; t < T; t++) inv_first_compute_store(&regs[t * 16], smem.data(), ht.inv.data(), q, t, s0, blk);
+            for (int k = 2; k >= 1; k--)
+                for (u32 w = 0; w < T / 32; w++) {
+                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); inv_mid_load(&regs[t * 16], smem.data(), c); }
+                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); inv_mid_compute(&regs[t * 16], ht.inv.data(), c, q); inv_mid_store(&regs[t * 16], smem.data(), c); }
+                }
+            for (u32 t = 0; t < T; t++) { PassCfg c = make_cfg(0, t, s0, blk); inv_mid_load(&regs[t * 16], smem.data(), c); }
+            for (u32 t = 0; t < T; t++) { PassCfg c = make_cfg(0, t, s0, blk); inv_final_compute_store(&regs[t * 16], out + (u64)blk * N, ht.inv.data(), c, q, t, s0, ht.ninv, ht.ninv_w1); }
+        }
+    }
+    return 0;
+}
+
+// worst 8-byte-bank conflict degree over all shared-memory access patterns of v2
+extern "C" int emu_bank_conflicts2() {
+    using namespace v2;
+    int worst = 1;
+    auto census = [&](u32* addr) {
+        for (int h = 0; h < 2; h++) {
+            int cnt[16] = {0};
+            for (int l = 0; l < 16; l++) cnt[addr[h * 16 + l] % 16]++;
+            for (int i = 0; i < 16; i++) worst = cnt[i] > worst ? cnt[i] : worst;
+        }
+    };
+    u32 addr[32];
+    for (u32 w = 0; w < T / 32; w++) {
+        for (int k = 0; k < 3; k++)
+            for (int r = 0; r < 16; r++) {
+                for (u32 l = 0; l < 32; l++) { PassCfg c = make_cfg(k, w * 32 + l, 0, 0); addr[l] = (u32)(r >> 2) * c.S4 + c.wl[r & 3]; }
+                census(addr);
+                for (u32 l = 0; l < 32; l++) { PassCfg c = make_cfg(k, w * 32 + l, 0, 0); addr[l] = (u32)(r >> 2) * c.S4 + c.ws[r & 3]; }
+                census(addr);
+            }
+        for (int g = 0; g < 4; g++)
+            for (int e = 0; e < 4; e++) {
+                for (u32 l = 0; l < 32; l++) addr[l] = last_slot(last_rest(w * 32 + l, g), e);
+                census(addr);
+                for (u32 l = 0; l < 32; l++) addr[l] = (brev_bits((u32)e, 2) << 12) | ((u32)g * T + w * 32 + l);  // inverse: flat natural read
+                census(addr);
+            }
+    }
+    return worst;
 }

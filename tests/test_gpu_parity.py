@@ -277,3 +277,83 @@ def test_error_paths():
         ctx.galois(ctx.empty((2, N)), 4)                           # even Galois element
     with pytest.raises(T.EngineError):
         T.Context(1 << 17, [97], [33])
+
+
+# ------------------------------------------------ kernel variants must all agree
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("harvey", [False, True])
+@pytest.mark.parametrize("logN,logqs", [(14, [60] * 8), (14, [60, 40, 40]), (15, [60, 60]), (16, [60]), (13, [60, 40])])
+def test_ntt_kernel_variants(version, harvey, logN, logqs):
+    N = 1 << logN
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(logN + version)
+    B = 40 if logN == 14 else 3           # > 148 rows: persistent CTAs loop over several rows
+    a = _rand(rng, N, qs, (B,))
+    a[0, 0, :] = qs[0] - 1                # worst case for the lazy ranges
+    want = orc.nntt(a)
+    T.ntt_version(version)
+    T.ntt_force_harvey(harvey)
+    try:
+        d = ctx.to_device(a)
+        f = ctx.ntt_fwd(d)
+        assert np.array_equal(H(f), want)
+        assert np.array_equal(H(ctx.ntt_inv(f)), a)
+        f2 = d.clone()
+        ctx.ntt_fwd(f2, out=f2)           # in place
+        assert np.array_equal(H(f2), want)
+        ctx.ntt_inv(f2, out=f2)
+        assert np.array_equal(H(f2), a)
+    finally:
+        T.ntt_version(1)
+        T.ntt_force_harvey(False)
+
+
+def test_non_lazy_primes_take_the_harvey_ladder():
+    # PALISADE prime 2^60 - 16383 (src/cryptparams.jl:25) is not of the form 2^b + small: Harvey path
+    q, N, psi = 1152921504606830593, 2048, 811032584449645127
+    ctx, orc = T.Context(N, [q], [psi]), CO.Rns(N, [q], [psi])
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, q, size=(4, 1, N), dtype=np.uint64)
+    a[0, 0, :] = q - 1
+    f = ctx.ntt_fwd(ctx.to_device(a))
+    assert np.array_equal(H(f), orc.nntt(a))
+    assert np.array_equal(H(ctx.ntt_inv(f)), a)
+    # a 61-bit prime close to 2^61 (no headroom for the lazy ladder)
+    N = 1 << 14
+    q = O.nextprime(2 ** 61 + 2 ** 59 + 1, 2 * N)
+    psi = T.minimal_primitive_root(q, 2 * N)
+    ctx, orc = T.Context(N, [q], [psi]), CO.Rns(N, [q], [psi])
+    a = rng.integers(0, q, size=(2, 1, N), dtype=np.uint64)
+    a[0, 0, :] = q - 1
+    f = ctx.ntt_fwd(ctx.to_device(a))
+    assert np.array_equal(H(f), orc.nntt(a))
+    assert np.array_equal(H(ctx.ntt_inv(f)), a)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_base_conversion_specialisations_agree(generic, q8, psi8):
+    N = 1024
+    allq, allpsi = T.prime_chain(N, [60] * 25)
+    qs, psis, qb, psib = allq[:8], allpsi[:8], allq[8:], allpsi[8:]
+    cq, cb = T.Context(N, qs, psis), T.Context(N, qb, psib)
+    oq, ob = CO.Rns(N, qs, psis), CO.Rns(N, qb, psib)
+    rng = np.random.default_rng(17)
+    c1, c2 = _rand(rng, N, qs, (2, 2)), _rand(rng, N, qs, (2, 2))
+    big = _rand(rng, N, qb, (3,))
+    Q, Qb = math.prod(qs), math.prod(qb)
+    for k, X in enumerate([Qb >> 1, (Qb >> 1) + 1, 0, 1, Qb - 1, Q >> 1, (Q >> 1) + 1, Q, Q - 1, Qb // 65537, Qb // 65537 + 1]):
+        for j, p in enumerate(qb):
+            big[0, j, k] = X % p
+    for k, X in enumerate([Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1]):
+        for i, q in enumerate(qs):
+            c1[0, 0, i, k] = X % q
+    T.force_generic(generic)
+    try:
+        assert np.array_equal(H(cq.bfv_switch(cb, cq.to_device(c1))), CO.bfv_switch(N, qs, qb, c1))
+        assert np.array_equal(H(cq.bfv_contract(cb, 65537, cb.to_device(big))), CO.bfv_contract(N, qs, qb, 65537, big))
+        # a plaintext modulus large enough that the sub-basis trick must fall back to the full basis
+        tbig = (1 << 61) - 1
+        assert np.array_equal(H(cq.bfv_contract(cb, tbig, cb.to_device(big))), CO.bfv_contract(N, qs, qb, tbig, big))
+        assert np.array_equal(H(cq.bfv_mul(cb, 65537, cq.to_device(c1), cq.to_device(c2))), CO.bfv_mul(oq, ob, 65537, c1, c2))
+    finally:
+        T.force_generic(False)

@@ -1,5 +1,6 @@
 // C-ABI of libtoyfhe_b200.so (see include/toyfhe_b200.h for the contract and the
 // reference methods each entry point replaces).
+#include <atomic>
 #include <cstring>
 
 #include "engine.h"
@@ -111,6 +112,20 @@ int tfb_profile_read(unsigned long long* counts, double* ms, int reset) {
     return TFB_OK;
 }
 int tfb_profile_classes(void) { return PC_COUNT; }
+int tfb_debug_ntt_version(int v) {
+    g_ntt_version = v == 2 ? 2 : 1;
+    return TFB_OK;
+}
+int tfb_debug_ntt_force_harvey(int on) {
+    extern bool g_ntt_force_harvey;
+    g_ntt_force_harvey = on != 0;
+    return TFB_OK;
+}
+int tfb_debug_force_generic(int on) {
+    extern bool g_force_generic;
+    g_force_generic = on != 0;
+    return TFB_OK;
+}
 const char* tfb_profile_class_name(int i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }
 
 const char* tfb_last_error(void) { return g_err.c_str(); }
@@ -188,6 +203,8 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     }
     TFB_CUDA(cudaSetDevice(device));
     tfb_ctx* c = new tfb_ctx();
+    static std::atomic<u64> next_uid{1};
+    c->uid = next_uid.fetch_add(1);
     c->device = device;
     c->N = N;
     c->L = L;
@@ -202,6 +219,8 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->ws = c->stage = c->io = nullptr;
     c->ws_bytes = c->stage_bytes = c->io_bytes = 0;
     c->conv_ok = false;
+    c->num_sms = 0;
+    c->ntt_mode = 1;
     std::vector<tw_t> fwd((size_t)L * N), inv((size_t)L * N);
     std::vector<PrimeParams> pp(L);
     for (uint32_t i = 0; i < L; i++) {
@@ -212,6 +231,12 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         pp[i].pc = ht.pc;
         pp[i].ninv = ht.ninv;
         pp[i].ninv_w1 = ht.ninv_w1;
+        u32 sh = 63 - (u32)__builtin_clzll(q[i]);
+        pp[i].sh = sh;
+        pp[i].pad_ = 0;
+        const u64 e = q[i] - (1ull << sh);
+        const bool lazy_ok = (e <= ((1ull << sh) >> 4)) && ((u128)q[i] * 15 < ((u128)1 << 64));
+        if (!lazy_ok) c->ntt_mode = 0;
     }
     int rc = TFB_OK;
     cudaError_t e;
@@ -224,6 +249,11 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         rc = tfb_cuda_fail(e, "ctx_create table upload");
     if (!rc) rc = build_garner(c);
     if (!rc) rc = ntt_setup_device();
+    if (!rc) rc = ntt2_setup_device();
+    if (!rc) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    }
     if (rc) {
         std::string keep = g_err;
         tfb_ctx_destroy(c);

@@ -12,11 +12,16 @@ struct PrimeParams {
     PrimeConst pc;
     tw_t ninv;     // N^-1
     tw_t ninv_w1;  // N^-1 * psi^-brev(1)
+    u32 sh;        // floor(log2 q) (shift of the lazy X reduction, ntt_core.cuh MODE 1)
+    u32 pad_;
 };
 
 struct tfb_ctx {
+    u64 uid;  // process-unique id (cache key for derived tables)
     int device;
     u32 N, logN, L;
+    int num_sms;
+    int ntt_mode;  // 0 = Harvey ladder, 1 = lazy ladder (all primes 2^b + small, 15q < 2^64)
     std::vector<u64> q, psi;
     tw_t* d_fwd;      // [L][N]
     tw_t* d_inv;      // [L][N]
@@ -83,5 +88,13 @@ int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* 
 int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch,
                             cudaStream_t st);
 int build_garner(tfb_ctx* c);
+// rns_fast.cu: specialised register-resident conversions; return false if no specialisation fits
+bool fast_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
+bool fast_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
 void tfb_forget_ctx_pairs(const tfb_ctx* c);
 int ntt_setup_device();
+// ntt_kernels2.cu
+int ntt2_setup_device();
+int launch_ntt14(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
+extern bool g_ntt_force_harvey;
+extern int g_ntt_version;  // 1 = 512x32 kernels everywhere, 2 = 1024x16 persistent kernels where available

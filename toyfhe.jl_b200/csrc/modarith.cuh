@@ -28,6 +28,8 @@ struct PrimeConst {
     u64 q2;       // 2q
     u64 br_hi;    // floor(2^128 / q) high word
     u64 br_lo;    // floor(2^128 / q) low word
+    u64 c64;      // 2^64 mod q
+    u64 c64p;     // Shoup companion floor(c64 * 2^64 / q)
 };
 
 #ifdef __CUDACC__
@@ -104,6 +106,18 @@ TFB_D u64 barrett_red64(u64 x, const PrimeConst& pc) {
     return csub(r, pc.q);
 }
 
+// (z1 * 2^64 + z0) mod q for ANY 128-bit value (needs q < 2^62): the high word goes
+// through a Shoup product with the constant 2^64 mod q, the low word through a
+// one-word Barrett step; canonical result.
+TFB_D u64 red128_any(u64 z1, u64 z0, const PrimeConst& pc) {
+    const u64 s = shoup_lazy(z1, pc.c64, pc.c64p, pc.q);       // [0,2q)
+    u64 r0 = z0 - mulhi64(z0, pc.br_hi) * pc.q;                // [0,3q)
+    r0 = csub(r0, pc.q2);                                      // [0,2q)
+    u64 t = s + r0;                                            // [0,4q)
+    t = csub(t, pc.q2);
+    return csub(t, pc.q);
+}
+
 TFB_D u64 add_mod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 TFB_D u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 TFB_D u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
@@ -138,5 +152,7 @@ static inline PrimeConst h_prime_const(u64 q) {
     u128 lo = (rem << 64) / q;
     pc.br_hi = (u64)hi;
     pc.br_lo = (u64)lo;
+    pc.c64 = (u64)(((u128)1 << 64) % q);
+    pc.c64p = h_shoup(pc.c64, q);
     return pc;
 }

@@ -65,6 +65,61 @@ TFB_HD void gs_bfly(u64& X, u64& Y, const tw_t w, const u64 q, const u64 q2) {
     Y = shoup_lazy(d, w.w, w.wp, q);
 }
 
+// ---- range policy of the forward ladder ---------------------------------
+// MODE 0 (Harvey): X is brought back to [0,2q) before every butterfly; needs q < 2^62.
+// MODE 1 (lazy):   for primes q = 2^b + e with 0 <= e <= 2^b/16 and 15q < 2^64 -- what
+//   nextprime(2^logq + 1) of the reference constructor yields (crt.jl:282-295) --
+//   values are left to grow by 2q per level ([0,Bq), B <= 14) and X is reduced once
+//   per pass with  x - (x >> b) q + q  in [q - 14e, 2q)  (5 instructions instead
+//   of a compare/select subtract at every level).  Shoup products accept any 64-bit Y.
+struct RedParams {
+    u64 q, q2, nq;  // q, 2q, -q (mod 2^64)
+    u32 sh;         // b = floor(log2 q)
+};
+TFB_HD RedParams make_red(const u64 q, const u32 sh) {
+    RedParams r;
+    r.q = q;
+    r.q2 = 2 * q;
+    r.nq = 0 - q;
+    r.sh = sh;
+    return r;
+}
+TFB_HD u64 reduce_shift(const u64 x, const RedParams& rp) {
+    const u64 k = x >> rp.sh;
+    return x + rp.q + k * rp.nq;
+}
+template <int MODE>
+TFB_HD u64 canon(const u64 v, const RedParams& rp) {
+    if (MODE == 0) return csub(csub(v, rp.q2), rp.q);
+    return csub(reduce_shift(v, rp), rp.q);
+}
+template <int MODE, bool RED>
+TFB_HD void ct_bfly_m(u64& X, u64& Y, const tw_t w, const RedParams& rp) {
+    u64 x = X;
+    if (MODE == 0) x = csub(x, rp.q2);
+    else if (RED) x = reduce_shift(x, rp);
+    const u64 t = shoup_lazy(Y, w.w, w.wp, rp.q);
+    X = x + t;
+    Y = x - t + rp.q2;
+}
+// LV levels; in MODE 1 the X operands are reduced at level 1 iff RED_FIRST
+template <int LV, int MODE, bool RED_FIRST>
+TFB_HD void ct_levels_m(u64* x, const tw_t* __restrict__ tw, const u32* tb, const RedParams& rp) {
+#pragma unroll
+    for (int u = 1; u <= LV; u++) {
+        const int half = (1 << LV) >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << (u - 1)); j++) {
+            const tw_t w = tw[tb[u - 1] + j];
+#pragma unroll
+            for (int k = 0; k < half; k++) {
+                if (u == 1 && RED_FIRST) ct_bfly_m<MODE, true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+                else ct_bfly_m<MODE, false>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+            }
+        }
+    }
+}
+
 // LV radix-2 CT levels over CNT=2^LV consecutive registers x[off..off+CNT);
 // level u (1..LV) block j uses twiddle tw[base(u) + j], base(u) = (lead << (u-1)) + ofs(u)
 // where the caller folds everything into `tb[u-1]`.
@@ -100,44 +155,41 @@ TFB_HD void gs_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const 
 // `in` points at the sub-block (Nsub = N contiguous positions); s0 = stages
 // already applied to the whole row (0 unless the row is longer than 2^14),
 // blk = index of this sub-block at level s0.
-template <int R>
+template <int R, int MODE>
 TFB_HD void fwd_phaseA(u64* x, const u64* __restrict__ in, u64* smem, const tw_t* __restrict__ tw,
-                       const u64 q, const u32 t, const u32 s0, const u32 blk) {
+                       const RedParams& rp, const u32 t, const u32 s0, const u32 blk) {
     typedef NttGeo<R> Geo;
-    const u64 q2 = 2 * q;
 #pragma unroll
     for (int a = 0; a < 32; a++) x[a] = in[a * Geo::T + t];
     u32 tb[5];
 #pragma unroll
     for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
-    ct_levels<5>(x, tw, tb, q, q2);
+    ct_levels_m<5, MODE, false>(x, tw, tb, rp);   // canonical input: bound 1 -> 11
 #pragma unroll
     for (int a = 0; a < 32; a++) smem[swz<R>(a, t)] = x[a];
 }
 
-template <int R>
-TFB_HD void fwd_phaseB(u64* x, u64* smem, const tw_t* __restrict__ tw, const u64 q, const u32 t,
+template <int R, int MODE>
+TFB_HD void fwd_phaseB(u64* x, u64* smem, const tw_t* __restrict__ tw, const RedParams& rp, const u32 t,
                        const u32 s0, const u32 blk) {
     typedef NttGeo<R> Geo;
-    const u64 q2 = 2 * q;
     const u32 a2 = t >> R, c2 = t & (Geo::RS - 1);
 #pragma unroll
     for (int b = 0; b < 32; b++) x[b] = smem[swz<R>(a2, b * Geo::RS + c2)];
     u32 tb[5];
 #pragma unroll
     for (int u = 1; u <= 5; u++) tb[u - 1] = (1u << (s0 + 4 + u)) + (blk << (4 + u)) + (a2 << (u - 1));
-    ct_levels<5>(x, tw, tb, q, q2);
+    ct_levels_m<5, MODE, true>(x, tw, tb, rp);    // bound 11 -> reduce -> 12
 #pragma unroll
     for (int b = 0; b < 32; b++) smem[swz<R>(a2, b * Geo::RS + c2)] = x[b];
 }
 
 // out points at the row base; the natural index of local position p is
 // (brev(p) << s0) + brev_s0(blk)
-template <int R>
+template <int R, int MODE>
 TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_t* __restrict__ tw,
-                       const u64 q, const u32 t, const u32 s0, const u32 blk) {
+                       const RedParams& rp, const u32 t, const u32 s0, const u32 blk) {
     typedef NttGeo<R> Geo;
-    const u64 q2 = 2 * q;
     const u32 w = t >> 5, lane = t & 31;
     const u32 a3 = brev_bits(lane, 5);
     const u32 oblk = brev_bits(blk, (int)s0);
@@ -152,15 +204,12 @@ TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_
 #pragma unroll
             for (int u = 1; u <= R; u++)
                 tb[u - 1] = (1u << (s0 + 9 + u)) + (blk << (9 + u)) + ((a3 * 32 + b3) << (u - 1));
-            ct_levels<R>(x + g * Geo::RS, tw, tb, q, q2);
+            ct_levels_m<R, MODE, true>(x + g * Geo::RS, tw, tb, rp);  // bound 12 -> reduce -> <= 10
         }
 #pragma unroll
         for (int c = 0; c < (int)Geo::RS; c++) {
             const u32 kl = (brev_bits((u32)c, R) << 10) | (k2 << 5) | lane;
-            u64 v = x[g * Geo::RS + c];
-            v = csub(v, q2);
-            v = csub(v, q);
-            out[((u64)kl << s0) + oblk] = v;
+            out[((u64)kl << s0) + oblk] = canon<MODE>(x[g * Geo::RS + c], rp);
         }
     }
 }

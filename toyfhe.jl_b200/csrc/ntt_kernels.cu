@@ -15,12 +15,14 @@
 #include "engine.h"
 #include "ntt_core.cuh"
 
+int g_ntt_version = 1;  // measured on B200: the 512x32 kernels beat the 1024x16 ones (tools/ntt_compare.py)
+bool g_ntt_force_harvey = false;
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
 void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 
 // ------------------------------------------------------------ row-resident
-template <int R>
+template <int R, int MODE>
 __global__ void __launch_bounds__(NttGeo<R>::T, 1)
 ntt_fwd_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
                    const PrimeParams* __restrict__ pp, const u32 L, const u32 s0) {
@@ -32,13 +34,13 @@ ntt_fwd_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
     const u32 prime = (u32)(row % L);
     const u64 nrow = (u64)Geo::N << s0;
     const tw_t* tw = tw_all + (u64)prime * nrow;
-    const u64 q = pp[prime].pc.q;
+    const RedParams rp = make_red(pp[prime].pc.q, pp[prime].sh);
     u64 x[32];
-    fwd_phaseA<R>(x, in + row * nrow + (u64)blk * Geo::N, smem, tw, q, t, s0, blk);
+    fwd_phaseA<R, MODE>(x, in + row * nrow + (u64)blk * Geo::N, smem, tw, rp, t, s0, blk);
     __syncthreads();
-    fwd_phaseB<R>(x, smem, tw, q, t, s0, blk);
+    fwd_phaseB<R, MODE>(x, smem, tw, rp, t, s0, blk);
     __syncthreads();
-    fwd_phaseC<R>(x, out + row * nrow, smem, tw, q, t, s0, blk);
+    fwd_phaseC<R, MODE>(x, out + row * nrow, smem, tw, rp, t, s0, blk);
 }
 
 template <int R>
@@ -162,8 +164,10 @@ static int launch_row(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool invers
     if (blocks > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
     if (inverse)
         { ProfScope ps(PC_NTT_INV, st); ntt_inv_row_kernel<R><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_inv, c->d_pp, c->L, s0); }
+    else if (c->ntt_mode == 1 && !g_ntt_force_harvey)
+        { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R, 1><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }
     else
-        { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }
+        { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R, 0><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
@@ -172,7 +176,8 @@ template <int R>
 static int setup_row() {
     const int smem = (int)(NttGeo<R>::N * sizeof(u64));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv_row_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_row_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_row_kernel<R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_row_kernel<R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return TFB_OK;
 }
 // opt in to >48 KiB dynamic shared memory on the current device (called per context)
@@ -209,6 +214,7 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
         TFB_CUDA(cudaGetLastError());
         return TFB_OK;
     }
+    if (logN == 14 && g_ntt_version == 2) return launch_ntt14(c, in, out, rows, inverse, 0, st);
     if (logN <= 14) return launch_row_dispatch(c, (int)logN - 10, in, out, rows, inverse, 0, st);
     if (logN > 16) { tfb_set_error("N > 2^16 is not supported"); return TFB_EUNSUPPORTED; }
     // long rows: s0 global levels + row-resident sub-blocks, through scratch
@@ -227,9 +233,10 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
             src = tmp;
         }
         TFB_CUDA(cudaGetLastError());
+        if (g_ntt_version == 2) return launch_ntt14(c, tmp, out, rows, false, s0, st);
         return launch_row_dispatch(c, 4, tmp, out, rows, false, s0, st);
     }
-    rc = launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
+    rc = g_ntt_version == 2 ? launch_ntt14(c, in, tmp, rows, true, s0, st) : launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
     if (rc) return rc;
     for (u32 s = s0; s >= 1; s--) {
         { ProfScope ps(PC_NTT_OTHER, st); ntt_inv_stage_kernel<<<nb, tb, 0, st>>>(tmp, s == 1 ? out : tmp, c->d_inv, c->d_pp, c->L, logN, s, total); }

@@ -17,6 +17,9 @@
 
 #define MAXD 32  // max primes in a basis that takes part in base conversion
 
+// testing hook: force the generic runtime-L kernels even where a specialisation exists
+bool g_force_generic = false;
+
 // 128-bit accumulator helpers ------------------------------------------------
 struct acc128 {
     u64 lo, hi;
@@ -28,8 +31,7 @@ __device__ __forceinline__ void mac128(acc128& a, u64 x, u64 y) {
 }
 // full reduction of a 128-bit value modulo q (any size of z)
 __device__ __forceinline__ u64 red128_full(acc128 a, const PrimeConst& pc) {
-    u64 h = barrett_red64(a.hi, pc);
-    return barrett_red128(h, a.lo, pc);
+    return red128_any(a.hi, a.lo, pc);
 }
 
 // ------------------------------------------------------------- elementwise
@@ -436,8 +438,10 @@ int launch_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 
     if (!polys) return TFB_OK;
     if (from->N != to->N) { tfb_set_error("base switch: ring degrees differ"); return TFB_EINVAL; }
     if (from->L > MAXD || !from->conv_ok) { tfb_set_error("base switch: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    int rc = TFB_OK;
+    if (!g_force_generic && fast_base_switch(from, to, in, out, polys, st, &rc)) return rc;
     PairTab pt;
-    int rc = get_pair(from, to, &pt);
+    rc = get_pair(from, to, &pt);
     if (rc) return rc;
     const u64 total = polys * from->N;
     const unsigned tb = 128;
@@ -505,8 +509,10 @@ int launch_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
     for (u32 i = 0; i < cq->L; i++)
         for (u32 j = 0; j < cb->L; j++)
             if (cq->q[i] == cb->q[j]) { tfb_set_error("bfv contract: the two bases must be disjoint"); return TFB_EINVAL; }
+    int rc = TFB_OK;
+    if (!g_force_generic && fast_bfv_contract(cq, cb, t, in, out, polys, st, &rc)) return rc;
     PairTab b2q, q2b, q2q;
-    int rc = get_pair(cb, cq, &b2q);
+    rc = get_pair(cb, cq, &b2q);
     if (rc) return rc;
     if ((rc = get_pair(cq, cb, &q2b))) return rc;
     if ((rc = get_pair(cq, cq, &q2q))) return rc;

@@ -22,6 +22,7 @@ _lib = None
 ABI_SYMBOLS = [
     "tfb_last_error", "tfb_version", "tfb_kernel_launches",
     "tfb_profile_enable", "tfb_profile_classes", "tfb_profile_class_name", "tfb_profile_read",
+    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey",
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
@@ -62,6 +63,21 @@ def _check(rc: int):
 
 def kernel_launches() -> int:
     return int(load_library().tfb_kernel_launches())
+
+
+def force_generic(on: bool) -> None:
+    """testing hook: use the generic base-conversion kernels instead of the specialised ones"""
+    _check(load_library().tfb_debug_force_generic(C.c_int(1 if on else 0)))
+
+
+def ntt_version(v: int) -> None:
+    """testing hook: select the row-kernel generation (1 or 2)"""
+    _check(load_library().tfb_debug_ntt_version(C.c_int(int(v))))
+
+
+def ntt_force_harvey(on: bool) -> None:
+    """testing hook: disable the lazy forward ladder"""
+    _check(load_library().tfb_debug_ntt_force_harvey(C.c_int(1 if on else 0)))
 
 
 def profile_enable(on: bool) -> None:
