@@ -12,3 +12,10 @@ from ._build import build_library
 
 __all__ = ["force_generic", "ntt_version", "ntt_force_harvey", "ABI_SYMBOLS", "LIB_PATH", "Context", "EngineError", "kernel_launches", "load_library",
            "minimal_primitive_root", "ndigits", "prime_chain", "profile_enable", "profile_read", "build_library"]
+
+from .ring import NegacyclicRing, RingElement, nntt, inntt
+from .scheme import (BFVParams, CKKSEncoding, CKKSParams, CKKSScale, CipherText, DropLastParams, EvalMultKey, GaloisKey,
+                     KeyComponent, KeyPair, KeySwitchKey, ModulusRaised, PrivKey, PubKey, Sampler, UsageError,
+                     apply_galois_element, ckks_mul_plain_vector, decrypt, enc_mul, encrypt, encrypt_zero,
+                     galois_element_from_steps, keygen, keygen_evalmult, keygen_galois, keyswitch, make_eval_key,
+                     modswitch, modswitch_drop, rotate)
