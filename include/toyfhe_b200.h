@@ -58,7 +58,8 @@ int tfb_profile_read(unsigned long long* counts, double* total_ms, int reset);
 /* testing hook: route base conversions through the generic runtime-L kernels even
  * where a register-resident specialisation exists (both must agree bit for bit) */
 int tfb_debug_force_generic(int on);
-/* kernel selection hook: 1 (default) = 512x32 row kernels, 2 = persistent TMA-prefetched 1024x16 kernels for N >= 2^14 */
+/* kernel selection hook for N >= 2^14: 1 = one CTA per row (512 threads x 32 residues), 2 = persistent TMA-prefetched
+ * 1024x16 kernels, 3 (default) = persistent TMA-prefetched 512x32 kernels */
 int tfb_debug_ntt_version(int v);
 /* testing hook: force the Harvey (conditional subtract per level) forward ladder even when every prime
  * qualifies for the lazy ladder */

@@ -20,13 +20,16 @@ static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
     HostTables ht;
     build_tables(Nrow, q, psi, ht);
     std::vector<u64> smem(Geo::N), regs((size_t)Geo::T * 32);
+    std::vector<tw_t> fwdc(Nrow), invc(Nrow);   // thread-order pass-3 copies, as tfb_ctx_create builds them
+    permute_pass3(ht.fwd.data(), fwdc.data(), 10 + R + (int)s0);
+    permute_pass3(ht.inv.data(), invc.data(), 10 + R + (int)s0);
     for (u32 blk = 0; blk < (1u << s0); blk++) {
         if (!inverse) {
             for (u32 t = 0; t < Geo::T; t++) fwd_phaseA<R, MODE>(&regs[t * 32], in + (u64)blk * Geo::N, smem.data(), ht.fwd.data(), rp, t, s0, blk);
             for (u32 t = 0; t < Geo::T; t++) fwd_phaseB<R, MODE>(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
-            for (u32 t = 0; t < Geo::T; t++) fwd_phaseC<R, MODE>(&regs[t * 32], out, smem.data(), ht.fwd.data(), rp, t, s0, blk);
+            for (u32 t = 0; t < Geo::T; t++) fwd_phaseC<R, MODE>(&regs[t * 32], out, smem.data(), fwdc.data(), rp, t, s0, blk);
         } else {
-            for (u32 t = 0; t < Geo::T; t++) inv_phaseC<R>(&regs[t * 32], in, smem.data(), ht.inv.data(), q, t, s0, blk);
+            for (u32 t = 0; t < Geo::T; t++) inv_phaseC<R>(&regs[t * 32], in, smem.data(), invc.data(), q, t, s0, blk);
             for (u32 t = 0; t < Geo::T; t++) inv_phaseB<R>(&regs[t * 32], smem.data(), ht.inv.data(), q, t, s0, blk);
             for (u32 t = 0; t < Geo::T; t++) inv_phaseA<R>(&regs[t * 32], out + (u64)blk * Geo::N, smem.data(), ht.inv.data(), q, t, s0, blk, ht.ninv, ht.ninv_w1);
         }

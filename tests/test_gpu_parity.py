@@ -280,7 +280,7 @@ def test_error_paths():
 
 
 # ------------------------------------------------ kernel variants must all agree
-@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("version", [1, 2, 3])
 @pytest.mark.parametrize("harvey", [False, True])
 @pytest.mark.parametrize("logN,logqs", [(14, [60] * 8), (14, [60, 40, 40]), (15, [60, 60]), (16, [60]), (13, [60, 40])])
 def test_ntt_kernel_variants(version, harvey, logN, logqs):
@@ -304,7 +304,7 @@ def test_ntt_kernel_variants(version, harvey, logN, logqs):
         ctx.ntt_inv(f2, out=f2)
         assert np.array_equal(H(f2), a)
     finally:
-        T.ntt_version(1)
+        T.ntt_version(3)
         T.ntt_force_harvey(False)
 
 

@@ -27,7 +27,7 @@ def timeit(fn, iters=20):
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
-for version in (1, 2):
+for version in (1, 2, 3):
     for harvey in (True, False):
         T.ntt_version(version)
         T.ntt_force_harvey(harvey)

@@ -113,7 +113,7 @@ int tfb_profile_read(unsigned long long* counts, double* ms, int reset) {
 }
 int tfb_profile_classes(void) { return PC_COUNT; }
 int tfb_debug_ntt_version(int v) {
-    g_ntt_version = v == 2 ? 2 : 1;
+    g_ntt_version = (v >= 1 && v <= 3) ? v : 3;
     return TFB_OK;
 }
 int tfb_debug_ntt_force_harvey(int on) {
@@ -185,6 +185,7 @@ int tfb_ndigits(const uint64_t* q, uint32_t L, uint32_t w, uint32_t* out) {
     return TFB_OK;
 }
 
+static inline u32 logN_of(u64 N) { u32 l = 0; while ((1ull << l) < N) l++; return l; }
 int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const uint64_t* psi, tfb_ctx** out) {
     if (!out || !q || !psi) { tfb_set_error("ctx_create: null argument"); return TFB_EINVAL; }
     *out = nullptr;
@@ -221,13 +222,16 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->conv_ok = false;
     c->num_sms = 0;
     c->ntt_mode = 1;
-    std::vector<tw_t> fwd((size_t)L * N), inv((size_t)L * N);
+    // [0, L*N): natural psi^brev(k) tables; [L*N, 2*L*N): thread-order copies for pass 3 (tables.h permute_pass3)
+    std::vector<tw_t> fwd((size_t)2 * L * N), inv((size_t)2 * L * N);
     std::vector<PrimeParams> pp(L);
     for (uint32_t i = 0; i < L; i++) {
         HostTables ht;
         build_tables(N, q[i], psi[i], ht);
         memcpy(&fwd[(size_t)i * N], ht.fwd.data(), (size_t)N * sizeof(tw_t));
         memcpy(&inv[(size_t)i * N], ht.inv.data(), (size_t)N * sizeof(tw_t));
+        permute_pass3(ht.fwd.data(), &fwd[(size_t)(L + i) * N], (int)logN_of(N));
+        permute_pass3(ht.inv.data(), &inv[(size_t)(L + i) * N], (int)logN_of(N));
         pp[i].pc = ht.pc;
         pp[i].ninv = ht.ninv;
         pp[i].ninv_w1 = ht.ninv_w1;
@@ -250,6 +254,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     if (!rc) rc = build_garner(c);
     if (!rc) rc = ntt_setup_device();
     if (!rc) rc = ntt2_setup_device();
+    if (!rc) rc = ntt3_setup_device();
     if (!rc) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;

@@ -96,5 +96,8 @@ int ntt_setup_device();
 // ntt_kernels2.cu
 int ntt2_setup_device();
 int launch_ntt14(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
+// ntt_kernels3.cu
+int ntt3_setup_device();
+int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
 extern bool g_ntt_force_harvey;
 extern int g_ntt_version;  // 1 = 512x32 kernels everywhere, 2 = 1024x16 persistent kernels where available

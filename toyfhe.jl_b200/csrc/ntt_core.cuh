@@ -51,6 +51,16 @@ TFB_HD u32 swz(u32 a, u32 idx) {
     return a * NttGeo<R>::T + (idx ^ (a >> 1));
 }
 
+// Pass-3 twiddles are read from a second copy of the table laid out in THREAD order
+// (host: permute_pass3 in tables.h): the twiddle of thread t, group g, level u, block j
+// of sub-block blk sits at  blk*N + (g*(RS-1) + 2^(u-1)-1 + j)*T + t,  so a warp's
+// 128-bit loads are contiguous (4 L1 wavefronts instead of 32 for the natural
+// psi^brev(k) order, whose pass-3 entries are 32*2^(u-1) apart between lanes).
+template <int R>
+TFB_HD u32 pass3_base(const u32 blk, const u32 g, const int u, const u32 t) {
+    return blk * NttGeo<R>::N + (g * (NttGeo<R>::RS - 1) + (1u << (u - 1)) - 1) * NttGeo<R>::T + t;
+}
+
 // Harvey lazy butterflies.  CT: X,Y in [0,4q) -> [0,4q).  GS: X,Y in [0,2q) -> [0,2q).
 TFB_HD void ct_bfly(u64& X, u64& Y, const tw_t w, const u64 q, const u64 q2) {
     u64 x = csub(X, q2);
@@ -104,13 +114,13 @@ TFB_HD void ct_bfly_m(u64& X, u64& Y, const tw_t w, const RedParams& rp) {
 }
 // LV levels; in MODE 1 the X operands are reduced at level 1 iff RED_FIRST
 template <int LV, int MODE, bool RED_FIRST>
-TFB_HD void ct_levels_m(u64* x, const tw_t* __restrict__ tw, const u32* tb, const RedParams& rp) {
+TFB_HD void ct_levels_m(u64* x, const tw_t* __restrict__ tw, const u32* tb, const RedParams& rp, const u32 js = 1) {
 #pragma unroll
     for (int u = 1; u <= LV; u++) {
         const int half = (1 << LV) >> u;
 #pragma unroll
         for (int j = 0; j < (1 << (u - 1)); j++) {
-            const tw_t w = tw[tb[u - 1] + j];
+            const tw_t w = tw[tb[u - 1] + j * js];
 #pragma unroll
             for (int k = 0; k < half; k++) {
                 if (u == 1 && RED_FIRST) ct_bfly_m<MODE, true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
@@ -138,13 +148,13 @@ TFB_HD void ct_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const 
 }
 // inverse order of the same ladder (levels LV..FIRST), GS butterflies
 template <int LV, int FIRST>
-TFB_HD void gs_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const u64 q, const u64 q2) {
+TFB_HD void gs_levels(u64* x, const tw_t* __restrict__ tw, const u32* tb, const u64 q, const u64 q2, const u32 js = 1) {
 #pragma unroll
     for (int u = LV; u >= FIRST; u--) {
         const int half = (1 << LV) >> u;
 #pragma unroll
         for (int j = 0; j < (1 << (u - 1)); j++) {
-            const tw_t w = tw[tb[u - 1] + j];
+            const tw_t w = tw[tb[u - 1] + j * js];
 #pragma unroll
             for (int k = 0; k < half; k++) gs_bfly(x[j * 2 * half + k], x[j * 2 * half + k + half], w, q, q2);
         }
@@ -187,7 +197,7 @@ TFB_HD void fwd_phaseB(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red
 // out points at the row base; the natural index of local position p is
 // (brev(p) << s0) + brev_s0(blk)
 template <int R, int MODE>
-TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_t* __restrict__ tw,
+TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_t* __restrict__ twc,
                        const RedParams& rp, const u32 t, const u32 s0, const u32 blk) {
     typedef NttGeo<R> Geo;
     const u32 w = t >> 5, lane = t & 31;
@@ -202,9 +212,8 @@ TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_
         if (R > 0) {
             u32 tb[R > 0 ? R : 1];
 #pragma unroll
-            for (int u = 1; u <= R; u++)
-                tb[u - 1] = (1u << (s0 + 9 + u)) + (blk << (9 + u)) + ((a3 * 32 + b3) << (u - 1));
-            ct_levels_m<R, MODE, true>(x + g * Geo::RS, tw, tb, rp);  // bound 12 -> reduce -> <= 10
+            for (int u = 1; u <= R; u++) tb[u - 1] = pass3_base<R>(blk, (u32)g, u, t);
+            ct_levels_m<R, MODE, true>(x + g * Geo::RS, twc, tb, rp, Geo::T);  // bound 12 -> reduce -> <= 10
         }
 #pragma unroll
         for (int c = 0; c < (int)Geo::RS; c++) {
@@ -218,7 +227,7 @@ TFB_HD void fwd_phaseC(u64* x, u64* __restrict__ out, const u64* smem, const tw_
 // itw = inverse table (psi^-brev(idx)); scale: N^-1 folded into the last level
 // when s0 == 0 (tn = Shoup pair of N^-1, twn = Shoup pair of N^-1 * itw[1]).
 template <int R>
-TFB_HD void inv_phaseC(u64* x, const u64* __restrict__ in, u64* smem, const tw_t* __restrict__ itw,
+TFB_HD void inv_phaseC(u64* x, const u64* __restrict__ in, u64* smem, const tw_t* __restrict__ itwc,
                        const u64 q, const u32 t, const u32 s0, const u32 blk) {
     typedef NttGeo<R> Geo;
     const u64 q2 = 2 * q;
@@ -237,9 +246,8 @@ TFB_HD void inv_phaseC(u64* x, const u64* __restrict__ in, u64* smem, const tw_t
         if (R > 0) {
             u32 tb[R > 0 ? R : 1];
 #pragma unroll
-            for (int u = 1; u <= R; u++)
-                tb[u - 1] = (1u << (s0 + 9 + u)) + (blk << (9 + u)) + ((a3 * 32 + b3) << (u - 1));
-            gs_levels<R, 1>(x + g * Geo::RS, itw, tb, q, q2);
+            for (int u = 1; u <= R; u++) tb[u - 1] = pass3_base<R>(blk, (u32)g, u, t);
+            gs_levels<R, 1>(x + g * Geo::RS, itwc, tb, q, q2, Geo::T);
         }
 #pragma unroll
         for (int c = 0; c < (int)Geo::RS; c++) smem[swz<R>(a3, b3 * Geo::RS + c)] = x[g * Geo::RS + c];

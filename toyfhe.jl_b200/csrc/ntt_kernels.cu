@@ -15,7 +15,7 @@
 #include "engine.h"
 #include "ntt_core.cuh"
 
-int g_ntt_version = 1;  // measured on B200: the 512x32 kernels beat the 1024x16 ones (tools/ntt_compare.py)
+int g_ntt_version = 3;  // 1 = one CTA per row (512x32), 2 = persistent 1024x16 + TMA, 3 = persistent 512x32 + TMA (tools/ntt_compare.py)
 bool g_ntt_force_harvey = false;
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
@@ -40,7 +40,7 @@ ntt_fwd_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
     __syncthreads();
     fwd_phaseB<R, MODE>(x, smem, tw, rp, t, s0, blk);
     __syncthreads();
-    fwd_phaseC<R, MODE>(x, out + row * nrow, smem, tw, rp, t, s0, blk);
+    fwd_phaseC<R, MODE>(x, out + row * nrow, smem, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
 }
 
 template <int R>
@@ -58,7 +58,7 @@ ntt_inv_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
     const PrimeParams P = pp[prime];
     const u64 q = P.pc.q;
     u64 x[32];
-    inv_phaseC<R>(x, in + row * nrow, smem, tw, q, t, s0, blk);
+    inv_phaseC<R>(x, in + row * nrow, smem, tw_all + (u64)(L + prime) * nrow, q, t, s0, blk);
     __syncthreads();
     inv_phaseB<R>(x, smem, tw, q, t, s0, blk);
     __syncthreads();
@@ -215,6 +215,7 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
         return TFB_OK;
     }
     if (logN == 14 && g_ntt_version == 2) return launch_ntt14(c, in, out, rows, inverse, 0, st);
+    if (logN == 14 && g_ntt_version == 3) return launch_ntt14p(c, in, out, rows, inverse, 0, st);
     if (logN <= 14) return launch_row_dispatch(c, (int)logN - 10, in, out, rows, inverse, 0, st);
     if (logN > 16) { tfb_set_error("N > 2^16 is not supported"); return TFB_EUNSUPPORTED; }
     // long rows: s0 global levels + row-resident sub-blocks, through scratch
@@ -234,6 +235,7 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
         }
         TFB_CUDA(cudaGetLastError());
         if (g_ntt_version == 2) return launch_ntt14(c, tmp, out, rows, false, s0, st);
+        if (g_ntt_version == 3) return launch_ntt14p(c, tmp, out, rows, false, s0, st);
         return launch_row_dispatch(c, 4, tmp, out, rows, false, s0, st);
     }
     rc = g_ntt_version == 2 ? launch_ntt14(c, in, tmp, rows, true, s0, st) : launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);

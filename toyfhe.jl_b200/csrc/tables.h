@@ -48,6 +48,29 @@ static inline void build_tables(u64 N, u64 q, u64 psi, HostTables& ht) {
     ht.pc = h_prime_const(q);
 }
 
+// Thread-order copy of the pass-3 twiddles of the row-resident kernels (ntt_core.cuh
+// pass3_base): rows of N = 2^logN words are processed as 2^s0 sub-blocks of 2^(10+R)
+// positions, R = min(logN,14)-10; thread t = (warp w, lane l) of sub-block blk handles,
+// in group g, the positions a = brev5(l), b = brev5(w*G+g) and uses at level u (1..R)
+// block j the natural-table entry 2^(s0+9+u) + blk*2^(9+u) + ((a*32+b) << (u-1)) + j.
+static inline void permute_pass3(const tw_t* src, tw_t* dst, int logN) {
+    const u64 N = 1ull << logN;
+    for (u64 i = 0; i < N; i++) dst[i] = src[0];
+    if (logN <= 10) return;
+    const int R = (logN > 14 ? 14 : logN) - 10, s0 = logN - 10 - R;
+    const u32 Nb = 1u << (10 + R), T = Nb / 32, RS = 1u << R, G = 32 / RS;
+    for (u32 blk = 0; blk < (1u << s0); blk++)
+        for (u32 g = 0; g < G; g++)
+            for (int u = 1; u <= R; u++)
+                for (u32 j = 0; j < (1u << (u - 1)); j++)
+                    for (u32 t = 0; t < T; t++) {
+                        const u32 a = h_brev(t & 31, 5), b = h_brev((t >> 5) * G + g, 5);
+                        const u64 from = (1ull << (s0 + 9 + u)) + ((u64)blk << (9 + u)) + ((u64)(a * 32 + b) << (u - 1)) + j;
+                        const u64 to = (u64)blk * Nb + (u64)(g * (RS - 1) + (1u << (u - 1)) - 1 + j) * T + t;
+                        dst[to] = src[from];
+                    }
+}
+
 // deterministic Miller-Rabin for 64-bit integers
 static inline bool h_is_prime(u64 n) {
     if (n < 2) return false;
