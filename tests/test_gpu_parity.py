@@ -189,6 +189,35 @@ def test_bfv_mul_headline_config(q8, psi8):
     assert np.array_equal(gm, CO.bfv_mul(oq, ob, 65537, c1, c2))
 
 
+@pytest.mark.parametrize("N,L,Lb,t", [(1024, 8, 17, 65537), (4096, 3, 7, 65537), (2048, 1, 3, 257), (64, 4, 9, 7), (256, 2, 6, 53)])
+def test_bfv_mul_joint_basis_equals_callers_basis(N, L, Lb, t):
+    """tfb_bfv_mul over its own extension basis Q u P' (first primes of R_big) vs the step-by-step
+    expand -> tensor -> contract over the caller's R_big (generic kernels) vs the oracle: identical,
+    including operands at the centring boundary (bfv.jl:202-220)."""
+    allq, allpsi = T.prime_chain(N, [60] * (L + Lb))
+    qs, psis, qb, psib = allq[:L], allpsi[:L], allq[L:], allpsi[L:]
+    cq, cb = T.Context(N, qs, psis), T.Context(N, qb, psib)
+    oq, ob = CO.Rns(N, qs, psis), CO.Rns(N, qb, psib)
+    rng = np.random.default_rng(7 * N + L)
+    c1, c2 = _rand(rng, N, qs, (3, 2)), _rand(rng, N, qs, (3, 2))
+    Q = math.prod(qs)
+    for k, X in enumerate([Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]):
+        for i, q in enumerate(qs):
+            c1[0, 0, i, k] = X % q
+            c2[1, 1, i, (k * 5) % N] = X % q
+    c1[2], c2[2] = c1[0], c1[0]                       # extreme magnitudes multiplied together
+    want = CO.bfv_mul(oq, ob, t, c1, c2)
+    d1, d2 = cq.to_device(c1), cq.to_device(c2)
+    fast = H(cq.bfv_mul(cb, t, d1, d2))
+    T.force_generic(True)
+    try:
+        slow = H(cq.bfv_mul(cb, t, d1, d2))
+    finally:
+        T.force_generic(False)
+    assert np.array_equal(fast, want)
+    assert np.array_equal(slow, want)
+
+
 # --------------------------------------------------------------------- key switching
 @pytest.mark.parametrize("w", [0, 1, 2, 7, 31])
 def test_keyswitch_digits(w):

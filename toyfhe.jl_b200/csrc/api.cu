@@ -53,6 +53,7 @@ int ws_reserve(tfb_ctx* c, size_t bytes) { return grow(&c->ws, &c->ws_bytes, byt
 int stage_reserve(tfb_ctx* c, size_t bytes) { return grow(&c->stage, &c->stage_bytes, bytes); }
 
 // ------------------------------------------------------------------ profiling
+#include <map>
 #include <mutex>
 static bool g_prof_on = false;
 static std::mutex g_prof_mu;
@@ -269,10 +270,12 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     return TFB_OK;
 }
 
+static void forget_joint(const tfb_ctx* c);
 int tfb_ctx_destroy(tfb_ctx* c) {
     if (!c) return TFB_OK;
     cudaSetDevice(c->device);
     tfb_forget_ctx_pairs(c);
+    forget_joint(c);
     cudaFree(c->d_fwd);
     cudaFree(c->d_inv);
     cudaFree(c->d_pp);
@@ -441,25 +444,88 @@ static u64 bfv_chunk(const tfb_ctx* cb, u64 batch) {
     return ch < batch ? ch : batch;
 }
 
+// joint context Q u P' (P' = first K primes of cb) owned by the library, cached per (cq, cb, K)
+struct JointKey {
+    u64 a, b;
+    int k;
+    bool operator<(const JointKey& o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : k < o.k); }
+};
+static std::map<JointKey, tfb_ctx*> g_joint;
+static std::mutex g_joint_mu;
+static void forget_joint(const tfb_ctx* c) {
+    std::vector<tfb_ctx*> dead;
+    {
+        std::lock_guard<std::mutex> lk(g_joint_mu);
+        for (auto it = g_joint.begin(); it != g_joint.end();) {
+            if (it->first.a == c->uid || it->first.b == c->uid) {
+                dead.push_back(it->second);
+                it = g_joint.erase(it);
+            } else
+                ++it;
+        }
+    }
+    for (tfb_ctx* j : dead) tfb_ctx_destroy(j);
+}
+static int joint_ctx(tfb_ctx* cq, tfb_ctx* cb, int K, tfb_ctx** out) {
+    std::lock_guard<std::mutex> lk(g_joint_mu);
+    JointKey key{cq->uid, cb->uid, K};
+    auto it = g_joint.find(key);
+    if (it != g_joint.end()) { *out = it->second; return TFB_OK; }
+    std::vector<u64> q(cq->q), psi(cq->psi);
+    q.insert(q.end(), cb->q.begin(), cb->q.begin() + K);
+    psi.insert(psi.end(), cb->psi.begin(), cb->psi.begin() + K);
+    tfb_ctx* j = nullptr;
+    int rc = tfb_ctx_create(cq->device, cq->N, (uint32_t)q.size(), q.data(), psi.data(), &j);
+    if (rc) return rc;
+    g_joint[key] = j;
+    *out = j;
+    return TFB_OK;
+}
+
+extern bool g_force_generic;
 int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(cq); CHECK_CTX(cb);
     if (!batch) return TFB_OK;
     CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
     if (cq->N != cb->N) { tfb_set_error("bfv_mul: ring degrees differ"); return TFB_EINVAL; }
+    if (t == 0) { tfb_set_error("bfv_mul: plaintext modulus is zero"); return TFB_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t polyq = (size_t)cq->L * cq->N, polyb = (size_t)cb->L * cb->N;
+    const size_t polyq = (size_t)cq->L * cq->N;
+    int rc;
+    const int K = g_force_generic ? 0 : fast_bfv_joint_k(cq, cb, t);
+    if (K > 0) {
+        // own extension basis Q u P' (rns_fast.cu "joint basis"): same integers, same result
+        tfb_ctx* cj = nullptr;
+        if ((rc = joint_ctx(cq, cb, K, &cj))) return rc;
+        const size_t polyj = (size_t)cj->L * cj->N;
+        const u64 ch = bfv_chunk(cj, batch);
+        if ((rc = ws_reserve(cj, 7 * ch * polyj * sizeof(u64)))) return rc;
+        u64* E1 = (u64*)cj->ws;
+        u64* T = E1 + 4 * ch * polyj;
+        for (u64 b0 = 0; b0 < batch; b0 += ch) {
+            const u64 nb = batch - b0 < ch ? batch - b0 : ch;
+            u64* E2 = E1 + 2 * nb * polyj;
+            if ((rc = fast_expand_joint(cq, cb, K, c1 + b0 * 2 * polyq, E1, 2 * nb, st))) return rc;
+            if ((rc = fast_expand_joint(cq, cb, K, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
+            if ((rc = launch_ntt(cj, E1, E1, 4 * nb * cj->L, false, st))) return rc;   // E1 and E2 are contiguous
+            if ((rc = launch_tensor_dual(cj, E1, E2, T, nb, st))) return rc;
+            if ((rc = launch_ntt(cj, T, T, 3 * nb * cj->L, true, st))) return rc;
+            if ((rc = fast_contract_joint(cq, cb, K, t, T, out + b0 * 3 * polyq, 3 * nb, st))) return rc;
+        }
+        return TFB_OK;
+    }
+    const size_t polyb = (size_t)cb->L * cb->N;
     const u64 ch = bfv_chunk(cb, batch);
-    int rc = ws_reserve(cb, 7 * ch * polyb * sizeof(u64));
+    rc = ws_reserve(cb, 7 * ch * polyb * sizeof(u64));
     if (rc) return rc;
     u64* E1 = (u64*)cb->ws;
-    u64* E2 = E1 + 2 * ch * polyb;
-    u64* T = E2 + 2 * ch * polyb;
+    u64* T = E1 + 4 * ch * polyb;
     for (u64 b0 = 0; b0 < batch; b0 += ch) {
         const u64 nb = batch - b0 < ch ? batch - b0 : ch;
+        u64* E2 = E1 + 2 * nb * polyb;
         if ((rc = launch_base_switch(cq, cb, c1 + b0 * 2 * polyq, E1, 2 * nb, st))) return rc;
         if ((rc = launch_base_switch(cq, cb, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
-        if ((rc = launch_ntt(cb, E1, E1, 2 * nb * cb->L, false, st))) return rc;
-        if ((rc = launch_ntt(cb, E2, E2, 2 * nb * cb->L, false, st))) return rc;
+        if ((rc = launch_ntt(cb, E1, E1, 4 * nb * cb->L, false, st))) return rc;   // E1 and E2 are contiguous
         if ((rc = launch_tensor_dual(cb, E1, E2, T, nb, st))) return rc;
         if ((rc = launch_ntt(cb, T, T, 3 * nb * cb->L, true, st))) return rc;
         if ((rc = launch_bfv_contract(cq, cb, t, T, out + b0 * 3 * polyq, 3 * nb, st))) return rc;

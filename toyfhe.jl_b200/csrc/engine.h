@@ -91,6 +91,10 @@ int build_garner(tfb_ctx* c);
 // rns_fast.cu: specialised register-resident conversions; return false if no specialisation fits
 bool fast_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
 bool fast_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
+// joint-basis BFV multiply (Q u first K primes of the big ring); K = 0: not applicable
+int fast_bfv_joint_k(const tfb_ctx* cq, const tfb_ctx* cb, u64 t);
+int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int fast_contract_joint(tfb_ctx* cq, tfb_ctx* cb, int K, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
 void tfb_forget_ctx_pairs(const tfb_ctx* c);
 int ntt_setup_device();
 // ntt_kernels2.cu

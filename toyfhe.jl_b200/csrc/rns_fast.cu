@@ -249,6 +249,220 @@ static int run_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
     return TFB_OK;
 }
 
+// ================================================================== joint basis
+// tfb_bfv_mul's own extension basis.  The value of a BFV product does not depend on
+// the big ring as long as the tensor integer x (|x| <= N Q^2 / 2 for canonical inputs)
+// and y = round(t x / Q) (|y| <= t N Q / 2 + 1) are represented without wrap-around
+// (bfv.jl:35-40,172-190 compute them over the integers).  So the fused multiply
+// works over Q u P', P' = the first K primes of the caller's big ring with
+// P' > 4 t N Q:  the Q-rows of the expanded operands are the inputs themselves,
+// only K new residues are computed per coefficient, and the contraction needs one
+// exact (non-centred) conversion r = (t x + h) mod Q -> P' and one centred
+// conversion y: P' -> Q whose overflow count is unambiguous (|y| < P'/4).
+//   expand_joint<L,K>   : [p][L][N] -> [p][L+K][N]   (rows 0..L-1 copied through)
+//   contract_joint<L,K> : [p][L+K][N] -> [p][L][N]
+template <int L, int K>
+struct ExpandJTab {
+    GarnerC<L> g;
+    u64 ev[K * L];   // (prod_{m<i} q_m) mod p_j
+    u64 qmod[K];     // Q mod p_j
+    PrimeConst pcb[K];
+};
+
+template <int L, int K>
+__global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
+                                                           const u64 total, const __grid_constant__ ExpandJTab<L, K> T) {
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & ((1u << logN) - 1));
+    u64 r[L], d[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        r[i] = in[((p * L + i) << logN) + n];
+        out[((p * (L + K) + i) << logN) + n] = r[i];
+    }
+    garner_reg<L, L>(r, d, T.g);
+    const bool neg = above_half_reg<L>(d, T.g);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        u64 v = eval_reg<L, L>(d, T.ev + j * L, T.pcb[j]);
+        if (neg) v = sub_mod(v, T.qmod[j], T.pcb[j].q);
+        out[((p * (L + K) + L + j) << logN) + n] = v;
+    }
+}
+
+template <int L, int K>
+struct ContractJTab {
+    GarnerC<L> gq;
+    tw_t t_q[L];             // t mod q_i
+    u64 h_q[L];              // floor(Q/2) mod q_i
+    u64 ev_qb[K * L];        // (prod_{m<i} q_m) mod p_j
+    tw_t t_b[K];             // t mod p_j
+    u64 h_b[K];              // floor(Q/2) mod p_j
+    tw_t comb[K];            // Q^-1 (P'/p_j)^-1 mod p_j
+    PrimeConst pcb[K];
+    u64 ev_bq[L * (K + 1)];  // (P'/p_j) mod q_i, j < K; then (-P') mod q_i
+    u32 sh[K];               // eta_j >> sh_j has at most 32 bits
+    u32 R[K];                // floor(2^(58+sh_j) / p_j)
+};
+
+template <int L, int K>
+__global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
+                                                             const u64 total, const __grid_constant__ ContractJTab<L, K> T) {
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & ((1u << logN) - 1));
+    // a = t x + h modulo every q_i; r = a mod Q as mixed-radix digits (exact, non-centred)
+    u64 a[L], d[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const u64 q = T.gq.pc[i].q;
+        const u64 x = in[((p * (L + K) + i) << logN) + n];
+        a[i] = add_mod(shoup_full(x, T.t_q[i].w, T.t_q[i].wp, q), T.h_q[i], q);
+    }
+    garner_reg<L, L>(a, d, T.gq);
+    // y = (a - r) / Q modulo p_j, pre-multiplied by (P'/p_j)^-1 for the CRT sum
+    u64 eta[K];
+    u64 F = 1ull << 57;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const PrimeConst& pc = T.pcb[j];
+        const u64 x = in[((p * (L + K) + L + j) << logN) + n];
+        const u64 aj = add_mod(shoup_full(x, T.t_b[j].w, T.t_b[j].wp, pc.q), T.h_b[j], pc.q);
+        const u64 rj = eval_reg<L, L>(d, T.ev_qb + j * L, pc);
+        eta[j] = shoup_full(sub_mod(aj, rj, pc.q), T.comb[j].w, T.comb[j].wp, pc.q);
+        F += (u64)(u32)(eta[j] >> T.sh[j]) * T.R[j];
+    }
+    // y = sum_j eta_j P'/p_j - w P' with w = round(sum_j eta_j / p_j): |y| < P'/4, so the
+    // 2^-21-accurate fixed-point sum F (scale 2^58) decides w without ambiguity
+    const u64 w = F >> 58;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const u64* ev = T.ev_bq + i * (K + 1);
+        u128 acc = (u128)w * ev[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) acc += (u128)eta[j] * ev[j];
+        out[((p * L + i) << logN) + n] = red128(acc, T.gq.pc[i]);
+    }
+}
+
+// number of leading primes of cb whose product exceeds 4 t N Q (0 if cb is too small
+// or a prime is below 2^32, which the fixed-point rounding above assumes)
+static int joint_basis_size(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
+    long double logQ = 0, logP = 0;
+    for (u32 i = 0; i < cq->L; i++) logQ += log2l((long double)cq->q[i]);
+    for (u32 k = 0; k < cb->L; k++) logP += log2l((long double)cb->q[k]);
+    // The caller's big ring must itself hold every tensor value without wrap-around (P > N Q^2);
+    // otherwise the reference's result depends on P (centred lift modulo P, bfv.jl:202-226) and
+    // only the conversion over the caller's own basis reproduces it.
+    if (logP <= (long double)cq->logN + 2 * logQ + 0.01L) return 0;
+    const long double need = 2.0L + 0.01L + log2l((long double)t) + (long double)cq->logN + logQ;
+    long double have = 0;
+    for (u32 k = 0; k < cb->L; k++) {
+        if (cb->q[k] < (1ull << 32)) return 0;
+        for (u32 i = 0; i < cq->L; i++) if (cq->q[i] == cb->q[k]) return 0;
+        have += log2l((long double)cb->q[k]);
+        if (have > need) return (int)k + 1;
+    }
+    return 0;
+}
+
+template <int L, int K>
+static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    typedef ExpandJTab<L, K> Tab;
+    static std::map<std::pair<u64, u64>, Tab> cache;
+    auto key = std::make_pair(cq->uid, cb->uid);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        Tab t;
+        fill_garner<L>(t.g, cq);
+        for (int j = 0; j < K; j++) {
+            fill_eval(t.ev + j * L, L, cq, cb->q[j], &t.qmod[j]);
+            t.pcb[j] = h_prime_const(cb->q[j]);
+        }
+        it = cache.emplace(key, t).first;
+    }
+    const u64 total = polys * cq->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_BASE_SWITCH, st); expand_joint_kernel<L, K><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+template <int L, int K>
+static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    typedef ContractJTab<L, K> Tab;
+    static std::map<std::tuple<u64, u64, u64>, Tab> cache;
+    auto key = std::make_tuple(cq->uid, cb->uid, t);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        Tab T;
+        fill_garner<L>(T.gq, cq);
+        for (int i = 0; i < L; i++) {
+            const u64 qi = cq->q[i];
+            T.t_q[i] = h_tw(t % qi, qi);
+            T.h_q[i] = half_mod(cq, qi);
+            u64 Pm = 1 % qi;   // P' mod q_i
+            for (int j = 0; j < K; j++) Pm = h_mulmod(Pm, cb->q[j] % qi, qi);
+            for (int j = 0; j < K; j++) {   // (P'/p_j) mod q_i
+                u64 M = 1 % qi;
+                for (int m = 0; m < K; m++) if (m != j) M = h_mulmod(M, cb->q[m] % qi, qi);
+                T.ev_bq[i * (K + 1) + j] = M;
+            }
+            T.ev_bq[i * (K + 1) + K] = Pm ? qi - Pm : 0;
+        }
+        for (int j = 0; j < K; j++) {
+            const u64 pj = cb->q[j];
+            u64 Qm;
+            fill_eval(T.ev_qb + j * L, L, cq, pj, &Qm);
+            T.t_b[j] = h_tw(t % pj, pj);
+            T.h_b[j] = half_mod(cq, pj);
+            u64 M = 1 % pj;   // (P'/p_j) mod p_j
+            for (int m = 0; m < K; m++) if (m != j) M = h_mulmod(M, cb->q[m] % pj, pj);
+            T.comb[j] = h_tw(h_invmod(h_mulmod(Qm, M, pj), pj), pj);
+            T.pcb[j] = h_prime_const(pj);
+            const u32 bits = 64 - (u32)__builtin_clzll(pj);
+            T.sh[j] = bits > 32 ? bits - 32 : 0;
+            T.R[j] = (u32)((((u128)1) << (58 + T.sh[j])) / pj);
+        }
+        it = cache.emplace(key, T).first;
+    }
+    const u64 total = polys * cq->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_BFV_CONTRACT, st); contract_joint_kernel<L, K><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+#define JOINT_CASES(X) X(1, 2) X(1, 3) X(2, 3) X(2, 4) X(3, 4) X(3, 5) X(4, 5) X(4, 6) X(8, 9) X(8, 10)
+// K > 0 when the joint-basis fast path applies to (cq, cb, t)
+int fast_bfv_joint_k(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
+    if (!cq->conv_ok || cq->N != cb->N) return 0;
+    const int K = joint_basis_size(cq, cb, t);
+#define JK(A, B) if ((int)cq->L == A && K == B) return K;
+    JOINT_CASES(JK)
+#undef JK
+    return 0;
+}
+int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+#define JE(A, B) if ((int)cq->L == A && K == B) return run_expand_joint<A, B>(cq, cb, in, out, polys, st);
+    JOINT_CASES(JE)
+#undef JE
+    tfb_set_error("internal: no joint expand kernel");
+    return TFB_EINVAL;
+}
+int fast_contract_joint(tfb_ctx* cq, tfb_ctx* cb, int K, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+#define JC(A, B) if ((int)cq->L == A && K == B) return run_contract_joint<A, B>(cq, cb, t, in, out, polys, st);
+    JOINT_CASES(JC)
+#undef JC
+    tfb_set_error("internal: no joint contract kernel");
+    return TFB_EINVAL;
+}
+
 // returns 1 if a specialised kernel handled the call, 0 if the caller must use the
 // generic path, <0 never; errors are reported through *rc
 bool fast_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc) {
