@@ -19,3 +19,4 @@ from .scheme import (BFVParams, CKKSEncoding, CKKSParams, CKKSScale, CipherText,
                      apply_galois_element, ckks_mul_plain_vector, decrypt, enc_mul, encrypt, encrypt_zero,
                      galois_element_from_steps, keygen, keygen_evalmult, keygen_galois, keyswitch, make_eval_key,
                      modswitch, modswitch_drop, rotate)
+from . import sharding

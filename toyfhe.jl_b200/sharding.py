@@ -1,0 +1,111 @@
+"""Ciphertext-parallel sharding across GPUs (one process per GPU, torch.distributed).
+
+The reference is single-process; its "batches" are plain `map`s over arrays of
+independent ciphertexts (examples/encrypted_mnist/infer.jl:120-137), and every
+ring operation is independent per ciphertext (and per RNS prime, crt.jl:250-254).
+So a batch shards over ranks with NO data-path collective: each rank runs the
+engine on its contiguous slice, context tables and evaluation keys are replicated.
+NCCL (or gloo in the CPU tests) is used only to scatter a batch that lives on one
+rank and to gather the results back.
+
+Layout: batches are int64/uint64 tensors `[batch, ...]` (engine layout
+`[batch][components][L][N]`); sharding is along dim 0.
+"""
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [start, stop) of `n_units` independent units for `rank`
+    (the first n_units % world ranks get one extra unit)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    if n_units < 0:
+        raise ValueError("n_units must be >= 0")
+    base, extra = divmod(n_units, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_units: int, world: int) -> List[int]:
+    return [shard_range(n_units, r, world)[1] - shard_range(n_units, r, world)[0] for r in range(world)]
+
+
+def _world(group=None) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def scatter_batch(full: Optional[torch.Tensor], batch: int, tail_shape: Sequence[int], dtype=torch.int64,
+                  device=None, src: int = 0, group=None) -> torch.Tensor:
+    """Rank `src` holds `full` = [batch, *tail_shape]; every rank gets its shard_range slice.
+    Ragged shards are sent point-to-point (scatter needs equal sizes)."""
+    rank, world = _world(group)
+    lo, hi = shard_range(batch, rank, world)
+    if world == 1:
+        return full[lo:hi].contiguous()
+    mine = torch.empty((hi - lo, *tail_shape), dtype=dtype, device=device)
+    if rank == src:
+        reqs = []
+        for r in range(world):
+            a, b = shard_range(batch, r, world)
+            if r == src:
+                mine.copy_(full[a:b])
+            elif b > a:
+                reqs.append(dist.isend(full[a:b].contiguous(), dst=r, group=group))
+        for q in reqs:
+            q.wait()
+    elif hi > lo:
+        dist.recv(mine, src=src, group=group)
+    return mine
+
+
+def gather_batch(local: torch.Tensor, batch: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Inverse of scatter_batch: rank `dst` returns [batch, ...], the others None."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    if rank == dst:
+        out = torch.empty((batch, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        for r in range(world):
+            a, b = shard_range(batch, r, world)
+            if r == dst:
+                out[a:b].copy_(local)
+            elif b > a:
+                dist.recv(out[a:b], src=r, group=group)
+        return out
+    if local.shape[0] > 0:
+        dist.send(local.contiguous(), dst=dst, group=group)
+    return None
+
+
+def sharded_apply(op: Callable[..., torch.Tensor], batch: int, inputs: Sequence[Optional[torch.Tensor]],
+                  tail_shapes: Sequence[Sequence[int]], device=None, root: int = 0, group=None) -> Optional[torch.Tensor]:
+    """scatter -> `op` on the local shard -> gather.  `op` is an engine call such as
+    `lambda a, b: ctx.bfv_mul(big, t, a, b)`; ranks with an empty shard skip it."""
+    rank, world = _world(group)
+    shards = [scatter_batch(x, batch, ts, device=device, src=root, group=group) for x, ts in zip(inputs, tail_shapes)]
+    if shards[0].shape[0] > 0:
+        res = op(*shards)
+        meta = torch.tensor(list(res.shape[1:]), dtype=torch.int64, device=res.device)
+    else:
+        res, meta = None, None
+    if world > 1:
+        # every rank needs the result's tail shape to build an empty shard / the gather buffer
+        lo0, hi0 = shard_range(batch, 0, world)
+        holder = 0 if hi0 > lo0 else None
+        if holder is None:
+            raise ValueError("empty batch")
+        n = torch.zeros(1, dtype=torch.int64, device=shards[0].device)
+        if rank == holder:
+            n[0] = meta.numel()
+        dist.broadcast(n, src=holder, group=group)
+        if rank != holder:
+            meta = torch.zeros(int(n.item()), dtype=torch.int64, device=shards[0].device)
+        dist.broadcast(meta, src=holder, group=group)
+        if res is None:
+            res = torch.empty((0, *[int(v) for v in meta.tolist()]), dtype=shards[0].dtype, device=shards[0].device)
+    return gather_batch(res, batch, dst=root, group=group)
