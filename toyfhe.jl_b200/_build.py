@@ -22,9 +22,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+        flags.append("-Xptxas=-v")
+    # one nvcc process per translation unit, in parallel (the unrolled kernels take ~1 min of ptxas in total)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        procs.append((src, obj, subprocess.Popen([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj],
+                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, failed = [], []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            failed.append((src, out))
+        objs.append(obj)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(f"--- {s}\n{o}" for s, o in failed))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB

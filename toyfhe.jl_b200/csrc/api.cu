@@ -271,11 +271,13 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
 }
 
 static void forget_joint(const tfb_ctx* c);
+static void forget_pipe(const tfb_ctx* c);
 int tfb_ctx_destroy(tfb_ctx* c) {
     if (!c) return TFB_OK;
     cudaSetDevice(c->device);
     tfb_forget_ctx_pairs(c);
     forget_joint(c);
+    forget_pipe(c);
     cudaFree(c->d_fwd);
     cudaFree(c->d_inv);
     cudaFree(c->d_pp);
@@ -662,20 +664,91 @@ int tfb_ct_tensor_host(tfb_ctx* c, const uint64_t* c1, const uint64_t* c2, uint6
     TFB_CUDA(cudaStreamSynchronize(st));
     return TFB_OK;
 }
+// Host-buffer BFV multiply, software-pipelined over chunks of the batch: copy-in, compute and
+// copy-out run on three internal streams with double-buffered device slots, so the two PCIe
+// directions and the kernels overlap (the one-shot version spent ~80% of its time in the copies).
+struct HostPipe {
+    cudaStream_t in = nullptr, cmp = nullptr, out = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, cmp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    cudaEvent_t entry = nullptr, exit_ = nullptr;
+    bool ok = false;
+};
+static std::map<u64, HostPipe> g_pipes;   // by context uid
+static std::mutex g_pipes_mu;
+static int host_pipe(tfb_ctx* c, HostPipe** out) {
+    std::lock_guard<std::mutex> lk(g_pipes_mu);
+    HostPipe& p = g_pipes[c->uid];
+    if (!p.ok) {
+        TFB_CUDA(cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking));
+        TFB_CUDA(cudaStreamCreateWithFlags(&p.cmp, cudaStreamNonBlocking));
+        TFB_CUDA(cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            TFB_CUDA(cudaEventCreateWithFlags(&p.h2d_done[i], cudaEventDisableTiming));
+            TFB_CUDA(cudaEventCreateWithFlags(&p.cmp_done[i], cudaEventDisableTiming));
+            TFB_CUDA(cudaEventCreateWithFlags(&p.d2h_done[i], cudaEventDisableTiming));
+        }
+        TFB_CUDA(cudaEventCreateWithFlags(&p.entry, cudaEventDisableTiming));
+        TFB_CUDA(cudaEventCreateWithFlags(&p.exit_, cudaEventDisableTiming));
+        p.ok = true;
+    }
+    *out = &p;
+    return TFB_OK;
+}
+static void forget_pipe(const tfb_ctx* c) {
+    std::lock_guard<std::mutex> lk(g_pipes_mu);
+    auto it = g_pipes.find(c->uid);
+    if (it == g_pipes.end()) return;
+    HostPipe& p = it->second;
+    if (p.ok) {
+        cudaStreamDestroy(p.in); cudaStreamDestroy(p.cmp); cudaStreamDestroy(p.out);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(p.h2d_done[i]); cudaEventDestroy(p.cmp_done[i]); cudaEventDestroy(p.d2h_done[i]); }
+        cudaEventDestroy(p.entry); cudaEventDestroy(p.exit_);
+    }
+    g_pipes.erase(it);
+}
+
 int tfb_bfv_mul_host(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(cq); CHECK_CTX(cb);
     if (!batch) return TFB_OK;
     CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t poly = (size_t)cq->L * cq->N;
-    u64* d;
-    int rc = io_buf(cq, 7 * batch * poly, &d);
+    // chunk: about 32 MiB of input per copy, at least one pair
+    u64 ch = (u64)((size_t)(32u << 20) / (4 * poly * sizeof(u64)));
+    if (ch < 1) ch = 1;
+    if (ch > batch) ch = batch;
+    HostPipe* P;
+    int rc = host_pipe(cq, &P);
     if (rc) return rc;
-    u64 *d1 = d, *d2 = d + 2 * batch * poly, *dout = d + 4 * batch * poly;
-    H2D(d1, c1, 2 * batch * poly);
-    H2D(d2, c2, 2 * batch * poly);
-    if ((rc = tfb_bfv_mul(cq, cb, t, d1, d2, dout, batch, stream))) return rc;
-    D2H(out, dout, 3 * batch * poly);
+    u64* d;
+    if ((rc = io_buf(cq, 2 * 7 * ch * poly, &d))) return rc;
+    u64* slot_in[2] = {d, d + 4 * ch * poly};
+    u64* slot_out[2] = {d + 8 * ch * poly, d + 11 * ch * poly};
+    TFB_CUDA(cudaEventRecord(P->entry, st));
+    TFB_CUDA(cudaStreamWaitEvent(P->in, P->entry, 0));
+    TFB_CUDA(cudaStreamWaitEvent(P->cmp, P->entry, 0));
+    TFB_CUDA(cudaStreamWaitEvent(P->out, P->entry, 0));
+    u64 idx = 0;
+    for (u64 b0 = 0; b0 < batch; b0 += ch, idx++) {
+        const u64 nb = batch - b0 < ch ? batch - b0 : ch;
+        const int s = (int)(idx & 1);
+        if (idx >= 2) TFB_CUDA(cudaStreamWaitEvent(P->in, P->cmp_done[s], 0));   // slot's previous compute has read it
+        TFB_CUDA(cudaMemcpyAsync(slot_in[s], c1 + b0 * 2 * poly, 2 * nb * poly * sizeof(u64), cudaMemcpyHostToDevice, P->in));
+        TFB_CUDA(cudaMemcpyAsync(slot_in[s] + 2 * nb * poly, c2 + b0 * 2 * poly, 2 * nb * poly * sizeof(u64), cudaMemcpyHostToDevice, P->in));
+        TFB_CUDA(cudaEventRecord(P->h2d_done[s], P->in));
+        TFB_CUDA(cudaStreamWaitEvent(P->cmp, P->h2d_done[s], 0));
+        if (idx >= 2) TFB_CUDA(cudaStreamWaitEvent(P->cmp, P->d2h_done[s], 0));  // slot's previous result has left
+        if ((rc = tfb_bfv_mul(cq, cb, t, slot_in[s], slot_in[s] + 2 * nb * poly, slot_out[s], nb, (void*)P->cmp))) return rc;
+        TFB_CUDA(cudaEventRecord(P->cmp_done[s], P->cmp));
+        TFB_CUDA(cudaStreamWaitEvent(P->out, P->cmp_done[s], 0));
+        TFB_CUDA(cudaMemcpyAsync(out + b0 * 3 * poly, slot_out[s], 3 * nb * poly * sizeof(u64), cudaMemcpyDeviceToHost, P->out));
+        TFB_CUDA(cudaEventRecord(P->d2h_done[s], P->out));
+    }
+    TFB_CUDA(cudaEventRecord(P->exit_, P->out));
+    TFB_CUDA(cudaStreamWaitEvent(st, P->exit_, 0));
+    TFB_CUDA(cudaStreamSynchronize(P->out));
+    TFB_CUDA(cudaStreamSynchronize(P->cmp));
+    TFB_CUDA(cudaStreamSynchronize(P->in));
     TFB_CUDA(cudaStreamSynchronize(st));
     return TFB_OK;
 }
