@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 engine on BASELINE.json's metric:
 homomorphic ciphertext multiplies/s (BFV, N=2^14, L=8 RNS primes, t=65537, R_big =
-17 further 60-bit primes: BASELINE configs[1]) plus the forward-NTT rate at the
+17 further 60-bit primes: BASELINE configs[1]; the engine multiplies over its own 17-prime joint basis
+Q u P', P' = the first 9 primes of R_big -- same integers, same result) plus the forward-NTT rate at the
 same (N, L).
 
   python bench.py --gpus N --steps K --warmup W          # our engine (one rank per GPU)
@@ -37,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -290,9 +291,20 @@ def run_ours(args):
     roofline = None
     if dom and "achieved_gbs" in kernels[dom]:
         a = kernels[dom]["achieved_gbs"]
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of this kernel from the committed ncu capture (same shape), scaled to this batch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if dom in tr:
+                traffic = float(tr[dom]) * B / float(tr["batch"])
+                traffic_src = "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
-                    "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
-                    "note": "61-bit modular butterflies: INT/FMA-pipe bound before HBM (see DESIGN.md)"}
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": alg[dom] // max(1, kernels[dom]["launches"] // K),
+                    "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
+                    "note": "61-bit modular butterflies: the FMA (IMAD) pipe is 72% busy at this rate -- pipe-bound before HBM "
+                            "(DESIGN.md section 5, profiles/r01_ncu_bfv_step.txt)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -311,7 +323,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * 2 * L_Q * Nb),
                 "d2h_bytes_per_step": int(Be * 3 * L_Q * Nb), "batch": Be, "ms_per_step": e2e_s * 1e3,
-                "api": "tfb_bfv_mul_host (pinned host buffers, H2D + compute + D2H per step)"},
+                "api": "tfb_bfv_mul_host (pinned host buffers; H2D, kernels and D2H pipelined over 8-pair chunks on three streams)"},
         "roofline": roofline,
         "kernels": kernels,
         "ntt_fwd": {"value": world * ntt_polys / (ntt_ms * 1e-3), "unit": "RNS-NTT/s (N=2^14, L=8)",

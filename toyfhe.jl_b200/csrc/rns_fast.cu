@@ -302,7 +302,7 @@ struct ContractJTab {
     u64 h_b[K];              // floor(Q/2) mod p_j
     tw_t comb[K];            // Q^-1 (P'/p_j)^-1 mod p_j
     PrimeConst pcb[K];
-    u64 ev_bq[L * (K + 1)];  // (P'/p_j) mod q_i, j < K; then (-P') mod q_i
+    u64 ev_bq[(K + 1) * L];  // [j*L + i] = (P'/p_j) mod q_i, j < K; [K*L + i] = (-P') mod q_i
     u32 sh[K];               // eta_j >> sh_j has at most 32 bits
     u32 R[K];                // floor(2^(58+sh_j) / p_j)
 };
@@ -324,27 +324,33 @@ __global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restri
     }
     garner_reg<L, L>(a, d, T.gq);
     // y = (a - r) / Q modulo p_j, pre-multiplied by (P'/p_j)^-1 for the CRT sum
-    u64 eta[K];
-    u64 F = 1ull << 57;
+    //   y = sum_j eta_j P'/p_j - w P',  w = round(sum_j eta_j / p_j)
+    // accumulated on the fly into one 128-bit sum per q_i.  The loop over j is NOT unrolled:
+    // fully unrolled the kernel is 68 KB of code and stalls 25% of the time on instruction
+    // fetch (profiles/r01_ncu_bfv_step.txt); the constants are indexed in the parameter bank.
+    u128 acc[L];
 #pragma unroll
+    for (int i = 0; i < L; i++) acc[i] = 0;
+    u64 F = 1ull << 57;
+#pragma unroll 1
     for (int j = 0; j < K; j++) {
-        const PrimeConst& pc = T.pcb[j];
+        const PrimeConst pc = T.pcb[j];
         const u64 x = in[((p * (L + K) + L + j) << logN) + n];
-        const u64 aj = add_mod(shoup_full(x, T.t_b[j].w, T.t_b[j].wp, pc.q), T.h_b[j], pc.q);
+        const tw_t tb = T.t_b[j], cm = T.comb[j];
+        const u64 aj = add_mod(shoup_full(x, tb.w, tb.wp, pc.q), T.h_b[j], pc.q);
         const u64 rj = eval_reg<L, L>(d, T.ev_qb + j * L, pc);
-        eta[j] = shoup_full(sub_mod(aj, rj, pc.q), T.comb[j].w, T.comb[j].wp, pc.q);
-        F += (u64)(u32)(eta[j] >> T.sh[j]) * T.R[j];
+        const u64 eta = shoup_full(sub_mod(aj, rj, pc.q), cm.w, cm.wp, pc.q);
+        F += (u64)(u32)(eta >> T.sh[j]) * T.R[j];
+        const u64* ev = T.ev_bq + j * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) acc[i] += (u128)eta * ev[i];
     }
-    // y = sum_j eta_j P'/p_j - w P' with w = round(sum_j eta_j / p_j): |y| < P'/4, so the
-    // 2^-21-accurate fixed-point sum F (scale 2^58) decides w without ambiguity
+    // |y| < P'/4, so the 2^-21-accurate fixed-point sum F (scale 2^58) decides w without ambiguity
     const u64 w = F >> 58;
 #pragma unroll
     for (int i = 0; i < L; i++) {
-        const u64* ev = T.ev_bq + i * (K + 1);
-        u128 acc = (u128)w * ev[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) acc += (u128)eta[j] * ev[j];
-        out[((p * L + i) << logN) + n] = red128(acc, T.gq.pc[i]);
+        acc[i] += (u128)w * T.ev_bq[K * L + i];
+        out[((p * L + i) << logN) + n] = red128(acc[i], T.gq.pc[i]);
     }
 }
 
@@ -410,9 +416,9 @@ static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u6
             for (int j = 0; j < K; j++) {   // (P'/p_j) mod q_i
                 u64 M = 1 % qi;
                 for (int m = 0; m < K; m++) if (m != j) M = h_mulmod(M, cb->q[m] % qi, qi);
-                T.ev_bq[i * (K + 1) + j] = M;
+                T.ev_bq[j * L + i] = M;
             }
-            T.ev_bq[i * (K + 1) + K] = Pm ? qi - Pm : 0;
+            T.ev_bq[K * L + i] = Pm ? qi - Pm : 0;
         }
         for (int j = 0; j < K; j++) {
             const u64 pj = cb->q[j];
