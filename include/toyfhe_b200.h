@@ -64,6 +64,9 @@ int tfb_debug_ntt_version(int v);
 /* testing hook: force the Harvey (conditional subtract per level) forward ladder even when every prime
  * qualifies for the lazy ladder */
 int tfb_debug_ntt_force_harvey(int on);
+/* testing hook: cap the forward-ladder range policy (0 = Harvey, 1 = lazy, 2 = lazy + approximate quotient,
+ * the default when every prime is 2^60 + e with e < 2^28); all must agree bit for bit */
+int tfb_debug_ntt_max_mode(int m);
 
 /* ---- ring construction helpers (host only, no GPU needed) ---------------- */
 /* NegacyclicRing(N, logqs) prime chain, crt.jl:282-295: ascending-logq order,

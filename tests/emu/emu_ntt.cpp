@@ -8,13 +8,16 @@
 
 #include "../../toyfhe.jl_b200/csrc/ntt_core.cuh"
 #include "../../toyfhe.jl_b200/csrc/ntt_core2.cuh"
+#include "../../toyfhe.jl_b200/csrc/ntt_core3.cuh"
 #include "../../toyfhe.jl_b200/csrc/tables.h"
 
 static u32 log2floor(u64 q) { return 63 - (u32)__builtin_clzll(q); }
 
 template <int R, int MODE>
 static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
-    const RedParams rp = make_red(q, log2floor(q));
+    u64 tab[16];
+    for (int k = 0; k < 16; k++) tab[k] = q - (u64)k * (q - (1ull << log2floor(q)));
+    const RedParams rp = MODE == 2 ? make_red2(q, log2floor(q), tab) : make_red(q, log2floor(q));
     typedef NttGeo<R> Geo;
     const u64 Nrow = (u64)Geo::N << s0;
     HostTables ht;
@@ -40,13 +43,20 @@ static void run(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
 // row-resident part is emulated: forward expects stages 1..s0 already applied to
 // `in`; inverse leaves stages s0..1 (and the N^-1 scale) to the caller.
 extern "C" int emu_ntt(int R, int mode, int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
-#define RUN(RR) case RR: if (mode) run<RR, 1>(inverse, q, psi, s0, in, out); else run<RR, 0>(inverse, q, psi, s0, in, out); break;
+#define RUN(RR) case RR: if (mode == 2) run<RR, 2>(inverse, q, psi, s0, in, out); else if (mode) run<RR, 1>(inverse, q, psi, s0, in, out); else run<RR, 0>(inverse, q, psi, s0, in, out); break;
     switch (R) {
         RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
         default: return 1;
     }
 #undef RUN
     return 0;
+}
+
+// number of lazy-range violations seen by the MODE 2 butterflies since the last call (must stay 0)
+extern "C" unsigned long long emu_overflow_count() {
+    const unsigned long long v = g_emu_overflow;
+    g_emu_overflow = 0;
+    return v;
 }
 
 // bank-conflict census of the three shared-memory access patterns (8-byte words,
@@ -164,6 +174,60 @@ extern "C" int emu_bank_conflicts2() {
                 for (u32 l = 0; l < 32; l++) addr[l] = (brev_bits((u32)e, 2) << 12) | ((u32)g * T + w * 32 + l);  // inverse: flat natural read
                 census(addr);
             }
+    }
+    return worst;
+}
+
+// ---- third-generation forward kernel (ntt_core3.cuh): skewed row buffer, approximate quotient, fused reductions.
+// Returns the number of lazy-range violations (must be 0).
+extern "C" long long emu_ntt3_fwd(u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+    using namespace v3;
+    if ((q >> 60) != 1 || q - (1ull << 60) >= (1ull << 28)) return -1;
+    redent_t tab[16];
+    fill_redtab(tab, q);
+    const Red3 rp = make_red3(q, tab);
+    const u64 Nrow = (u64)Geo::N << s0;
+    HostTables ht;
+    build_tables(Nrow, q, psi, ht);
+    std::vector<tw_t> fwdc(Nrow);
+    permute_pass3(ht.fwd.data(), fwdc.data(), 14 + (int)s0);
+    std::vector<u64> smem(ROW_WORDS), regs((size_t)Geo::T * 32);
+    g_emu_overflow3 = 0;
+    for (u32 blk = 0; blk < (1u << s0); blk++) {
+        for (u32 a = 0; a < 32; a++) memcpy(&smem[slot(a, 0)], in + (u64)blk * Geo::N + a * Geo::T, Geo::T * 8);   // the 32 bulk copies
+        for (u32 t = 0; t < Geo::T; t++) pass1(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
+        for (u32 t = 0; t < Geo::T; t++) pass2(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
+        for (u32 t = 0; t < Geo::T; t++) pass3_load(&regs[t * 32], smem.data(), t);
+        for (u32 t = 0; t < Geo::T; t++) {
+            if (s0 == 0) pass3_compute_store<true>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
+            else pass3_compute_store<false>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
+        }
+    }
+    return (long long)g_emu_overflow3;
+}
+// bank census of the skewed layout: 64-bit accesses per half-warp (passes 1, 2), 128-bit per quarter-warp (pass 3)
+extern "C" int emu_bank_conflicts3() {
+    using namespace v3;
+    int worst = 1;
+    for (u32 wbase = 0; wbase < Geo::T; wbase += 32) {
+        for (u32 r = 0; r < 32; r++)
+            for (int h = 0; h < 2; h++) {
+                int c1[16] = {0}, c2[16] = {0};
+                for (int l = 0; l < 16; l++) {
+                    const u32 t = wbase + h * 16 + l;
+                    c1[slot(r, t) % 16]++;
+                    c2[slot(t >> 4, r * 16 + (t & 15)) % 16]++;
+                }
+                for (int i = 0; i < 16; i++) { worst = c1[i] > worst ? c1[i] : worst; worst = c2[i] > worst ? c2[i] : worst; }
+            }
+        const u32 w = wbase >> 5;
+        for (u32 g = 0; g < 2; g++)
+            for (u32 c = 0; c < 16; c += 2)
+                for (int qw = 0; qw < 4; qw++) {
+                    int cnt[8] = {0};
+                    for (int l = 0; l < 8; l++) cnt[(slot(brev_bits(qw * 8 + l, 5), brev_bits(2 * w + g, 5) * 16 + c) / 2) % 8]++;
+                    for (int i = 0; i < 8; i++) worst = cnt[i] > worst ? cnt[i] : worst;
+                }
     }
     return worst;
 }

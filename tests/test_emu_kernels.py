@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 @pytest.fixture(scope="module")
 def emu():
     csrc = os.path.join(os.path.dirname(HERE), "toyfhe.jl_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("ntt_core.cuh", "ntt_core2.cuh", "modarith.cuh", "tables.h")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("ntt_core.cuh", "ntt_core2.cuh", "ntt_core3.cuh", "modarith.cuh", "tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return C.CDLL(LIB)
@@ -111,6 +111,53 @@ def test_v2_row_kernel(emu, mode):
         assert np.array_equal(back, a)
 
 
+@pytest.mark.parametrize("R", [0, 2, 4])
+def test_v1_row_kernels_mode2_approximate_quotient(emu, R):
+    """MODE 2 ladder (shoup_lazy4, T in [0,4q), table reduction of X at fixed levels) on 2^60 + e primes:
+    bit-exact against the oracle and no lazy-range violation on random, all-(q-1) and alternating rows."""
+    N = 1 << (10 + R)
+    emu.emu_overflow_count.restype = C.c_ulonglong
+    qs, psis = O.prime_chain(N, (60,) * 17)
+    for i in (0, 16):
+        q, psi = qs[i], psis[i]
+        assert q >> 60 == 1 and q - (1 << 60) < 1 << 28
+        orc = CO.Rns(N, [q], [psi])
+        rng = np.random.default_rng(R + i)
+        rows = [rng.integers(0, q, size=N, dtype=np.uint64), np.full(N, q - 1, dtype=np.uint64),
+                np.where(np.arange(N) % 2 == 0, q - 1, 0).astype(np.uint64)]
+        for a in rows:
+            a = np.ascontiguousarray(a.reshape(1, N))
+            got = np.zeros_like(a)
+            emu.emu_overflow_count()
+            assert emu.emu_ntt(R, 2, 0, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(a), P(got)) == 0
+            assert emu.emu_overflow_count() == 0
+            assert np.array_equal(got, orc.nntt(a))
+
+
+@pytest.mark.parametrize("s0", [0, 1])
+def test_v3_forward_kernel(emu, s0):
+    """third-generation forward kernel (skewed row buffer, approximate quotient, reductions fused into the
+    butterfly adds): bit-exact and inside its lazy ranges on random and extreme rows, first and last chain prime"""
+    N = 1 << (14 + s0)
+    emu.emu_ntt3_fwd.restype = C.c_longlong
+    qs, psis = O.prime_chain(N, (60,) * 17)
+    for i in (0, 16):
+        q, psi = qs[i], psis[i]
+        orc = CO.Rns(N, [q], [psi])
+        rng = np.random.default_rng(s0 * 7 + i)
+        rows = [rng.integers(0, q, size=N, dtype=np.uint64), np.full(N, q - 1, dtype=np.uint64),
+                np.where(np.arange(N) % 2 == 0, q - 1, 0).astype(np.uint64),
+                np.where(np.arange(N) < N // 2, q - 1, 1).astype(np.uint64)]
+        for a in rows[: 4 if s0 == 0 else 2]:
+            a = np.ascontiguousarray(a.reshape(1, N))
+            staged = np.ascontiguousarray(fwd_global_stages(a[0], q, psi, s0)).reshape(1, N) if s0 else a
+            got = np.zeros_like(a)
+            assert emu.emu_ntt3_fwd(C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got)) == 0
+            assert np.array_equal(got, orc.nntt(a))
+    q40, psi40 = O.prime_chain(1 << 14, (40,))
+    assert emu.emu_ntt3_fwd(C.c_uint64(q40[0]), C.c_uint64(psi40[0]), C.c_uint32(0), P(got), P(got)) == -1   # not a 2^60 + e prime
+
+
 def test_worst_case_inputs_lazy_bounds(emu):
     """all-(q-1) rows maximise every lazy intermediate: the lazy ladder must not wrap 2^64"""
     N = 1 << 14
@@ -149,3 +196,4 @@ def test_long_rows_as_sub_blocks(emu, s0, gen):
 def test_shared_memory_layouts_are_conflict_free(emu):
     assert emu.emu_bank_conflicts(4) == 1      # 512x32 kernel at N = 2^14
     assert emu.emu_bank_conflicts2() == 1      # 1024x16 kernel
+    assert emu.emu_bank_conflicts3() == 1      # skewed layout of the third-generation forward kernel

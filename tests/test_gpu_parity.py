@@ -309,10 +309,9 @@ def test_error_paths():
 
 
 # ------------------------------------------------ kernel variants must all agree
-@pytest.mark.parametrize("version", [1, 2, 3])
-@pytest.mark.parametrize("harvey", [False, True])
+@pytest.mark.parametrize("version,mode", [(1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)])
 @pytest.mark.parametrize("logN,logqs", [(14, [60] * 8), (14, [60, 40, 40]), (15, [60, 60]), (16, [60]), (13, [60, 40])])
-def test_ntt_kernel_variants(version, harvey, logN, logqs):
+def test_ntt_kernel_variants(version, mode, logN, logqs):
     N = 1 << logN
     qs, psis, ctx, orc = _ring(N, logqs)
     rng = np.random.default_rng(logN + version)
@@ -321,7 +320,7 @@ def test_ntt_kernel_variants(version, harvey, logN, logqs):
     a[0, 0, :] = qs[0] - 1                # worst case for the lazy ranges
     want = orc.nntt(a)
     T.ntt_version(version)
-    T.ntt_force_harvey(harvey)
+    T.ntt_max_mode(mode)
     try:
         d = ctx.to_device(a)
         f = ctx.ntt_fwd(d)
@@ -334,7 +333,7 @@ def test_ntt_kernel_variants(version, harvey, logN, logqs):
         assert np.array_equal(H(f2), a)
     finally:
         T.ntt_version(3)
-        T.ntt_force_harvey(False)
+        T.ntt_max_mode(2)
 
 
 def test_non_lazy_primes_take_the_harvey_ladder():

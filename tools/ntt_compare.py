@@ -27,11 +27,11 @@ def timeit(fn, iters=20):
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
-for version in (1, 2, 3):
-    for harvey in (True, False):
+for version, mode in ((1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)):
+    if True:
         T.ntt_version(version)
-        T.ntt_force_harvey(harvey)
+        T.ntt_max_mode(mode)
         f = timeit(lambda: cq.ntt_fwd(a, out=out))
         i = timeit(lambda: cq.ntt_inv(a, out=out))
-        print(f"v{version} {'harvey' if harvey else 'lazy  '}: fwd {f:.3f} ms = {rows / f / 1e3:.2f} Mrows/s {nbytes / f / 1e6:.0f} GB/s | "
+        print(f"v{version} mode {mode} ({('harvey', 'lazy', 'lazy+approx quotient')[mode]}): fwd {f:.3f} ms = {rows / f / 1e3:.2f} Mrows/s {nbytes / f / 1e6:.0f} GB/s | "
               f"inv {i:.3f} ms = {rows / i / 1e3:.2f} Mrows/s {nbytes / i / 1e6:.0f} GB/s", flush=True)

@@ -117,6 +117,10 @@ int tfb_debug_ntt_version(int v) {
     g_ntt_version = (v >= 1 && v <= 3) ? v : 3;
     return TFB_OK;
 }
+int tfb_debug_ntt_max_mode(int m) {
+    g_ntt_max_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
+    return TFB_OK;
+}
 int tfb_debug_ntt_force_harvey(int on) {
     extern bool g_ntt_force_harvey;
     g_ntt_force_harvey = on != 0;
@@ -223,6 +227,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->conv_ok = false;
     c->num_sms = 0;
     c->ntt_mode = 1;
+    bool all60 = true;
     // [0, L*N): natural psi^brev(k) tables; [L*N, 2*L*N): thread-order copies for pass 3 (tables.h permute_pass3)
     std::vector<tw_t> fwd((size_t)2 * L * N), inv((size_t)2 * L * N);
     std::vector<PrimeParams> pp(L);
@@ -242,7 +247,9 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         const u64 e = q[i] - (1ull << sh);
         const bool lazy_ok = (e <= ((1ull << sh) >> 4)) && ((u128)q[i] * 15 < ((u128)1 << 64));
         if (!lazy_ok) c->ntt_mode = 0;
+        if (sh != 60 || e >= (1ull << 28)) all60 = false;
     }
+    if (c->ntt_mode == 1 && all60) c->ntt_mode = 2;   // approximate-quotient ladder (ntt_core.cuh MODE 2)
     int rc = TFB_OK;
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_fwd, fwd.size() * sizeof(tw_t))) != cudaSuccess ||

@@ -79,6 +79,43 @@ TFB_D u64 shoup_lazy(u64 x, u64 w, u64 wp, u64 q) {
 }
 TFB_D u64 shoup_lazy(u64 x, tw_t t, u64 q) { return shoup_lazy(x, t.w, t.wp, q); }
 
+// x*w mod q in [0,4q) for primes q = 2^b + e with b >= 32 and e < 2^32 (what the reference's
+// nextprime(2^logq + 1) chains give, crt.jl:282-295); valid for ANY 64-bit x.
+//   quotient: h~ = x1*p1 + hi32(x1*p0) + hi32(x0*p1)  in [h-2, h]  (1 IMAD.WIDE + 2 IMAD.HI instead of the
+//             4 IMAD.WIDE of an exact 64x64 high product),
+//   tail:     x*w - h~*q = x*w - h~*e - (h~ << b)  (mod 2^64): one IMAD.WIDE less than a generic q.
+// ne = 2^32 - e, SHB = b - 32.  Measured on the FMA-heavy pipe (IMAD.WIDE/IMAD.HI 4 cycles, IMAD 2 cycles
+// per warp instruction, tools/bfly_bench4.cu): 30.8 instead of 34.8 pipe cycles per butterfly.
+template <int SHB>
+TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne) {
+#ifdef __CUDA_ARCH__
+    u32 x0, x1, w0, w1, p0, p1, h0, h1, a, b, lo, hi;
+    u64 t, acc;
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(x0), "=r"(x1) : "l"(x));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(w0), "=r"(w1) : "l"(w));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(p0), "=r"(p1) : "l"(wp));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x1), "r"(p1));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(a) : "r"(x1), "r"(p0));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(b) : "r"(x0), "r"(p1));
+    // ptxas folds the first high word into the IMAD.WIDE addend and the second into a carry-out IMAD.HI
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(h0), "=r"(h1) : "l"(t + (u64)a + (u64)b));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(x0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(ne));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x1), "r"(w0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(ne));
+    hi = hi - h0 - (h0 << SHB);
+    asm("mov.b64 %0, {%1,%2};" : "=l"(acc) : "r"(lo), "r"(hi));
+    return acc;
+#else
+    const u64 x1 = x >> 32, x0 = x & 0xffffffffu, p1 = wp >> 32, p0 = wp & 0xffffffffu;
+    const u64 h = x1 * p1 + ((x1 * p0) >> 32) + ((x0 * p1) >> 32);
+    (void)ne;
+    return x * w - h * q;
+#endif
+}
+
 // conditional subtract: x in [0,2m) -> [0,m)
 TFB_D u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
 

@@ -82,9 +82,19 @@ TFB_HD void gs_bfly(u64& X, u64& Y, const tw_t w, const u64 q, const u64 q2) {
 //   values are left to grow by 2q per level ([0,Bq), B <= 14) and X is reduced once
 //   per pass with  x - (x >> b) q + q  in [q - 14e, 2q)  (5 instructions instead
 //   of a compare/select subtract at every level).  Shoup products accept any 64-bit Y.
+// MODE 2 (lazy, approximate quotient): primes q = 2^60 + e, e < 2^28.  Shoup products use shoup_lazy4
+//   (T in [0,4q)), values grow by 4q per level and the X operands are reduced at levels 4 of pass 1,
+//   1 and 4 of passes 2 and 3 with a 16-entry table  x -> (x mod 2^60) + (q - (x >> 60) e)  in (0,2q):
+//   5 ALU/LSU instructions, nothing on the FMA-heavy pipe that bounds the kernel.
+#ifndef __CUDA_ARCH__
+static unsigned long long g_emu_overflow = 0;
+#endif
 struct RedParams {
     u64 q, q2, nq;  // q, 2q, -q (mod 2^64)
     u32 sh;         // b = floor(log2 q)
+    u32 ne, shb;    // MODE 2: 2^32 - e, b - 32
+    u64 q4;         // MODE 2: 4q
+    const u64* tab; // MODE 2: tab[k] = q - k e, k = 0..15 (shared memory in the kernels)
 };
 TFB_HD RedParams make_red(const u64 q, const u32 sh) {
     RedParams r;
@@ -92,7 +102,20 @@ TFB_HD RedParams make_red(const u64 q, const u32 sh) {
     r.q2 = 2 * q;
     r.nq = 0 - q;
     r.sh = sh;
+    r.ne = 0; r.shb = 0; r.q4 = 0; r.tab = nullptr;
     return r;
+}
+TFB_HD RedParams make_red2(const u64 q, const u32 sh, const u64* tab) {
+    RedParams r = make_red(q, sh);
+    r.ne = 0u - (u32)(q - (1ull << sh));
+    r.shb = sh - 32;
+    r.q4 = 4 * q;
+    r.tab = tab;
+    return r;
+}
+// x in [0,16q) -> (0,2q), same residue (q = 2^60 + e)
+TFB_HD u64 reduce_tab(const u64 x, const RedParams& rp) {
+    return (x & 0x0fffffffffffffffull) + rp.tab[x >> 60];
 }
 TFB_HD u64 reduce_shift(const u64 x, const RedParams& rp) {
     const u64 k = x >> rp.sh;
@@ -101,11 +124,22 @@ TFB_HD u64 reduce_shift(const u64 x, const RedParams& rp) {
 template <int MODE>
 TFB_HD u64 canon(const u64 v, const RedParams& rp) {
     if (MODE == 0) return csub(csub(v, rp.q2), rp.q);
+    if (MODE == 2) return csub(reduce_tab(v, rp), rp.q);
     return csub(reduce_shift(v, rp), rp.q);
 }
 template <int MODE, bool RED>
 TFB_HD void ct_bfly_m(u64& X, u64& Y, const tw_t w, const RedParams& rp) {
     u64 x = X;
+    if (MODE == 2) {
+        if (RED) x = reduce_tab(x, rp);
+        const u64 t = shoup_lazy4<28>(Y, w.w, w.wp, rp.q, rp.ne);
+#ifndef __CUDA_ARCH__
+        if (t >= rp.q4 || x + t < x || (((u128)x + rp.q4 - t) >> 64) != 0) g_emu_overflow++;   // tests/emu: the lazy bounds must hold
+#endif
+        X = x + t;
+        Y = x - t + rp.q4;
+        return;
+    }
     if (MODE == 0) x = csub(x, rp.q2);
     else if (RED) x = reduce_shift(x, rp);
     const u64 t = shoup_lazy(Y, w.w, w.wp, rp.q);
@@ -123,7 +157,7 @@ TFB_HD void ct_levels_m(u64* x, const tw_t* __restrict__ tw, const u32* tb, cons
             const tw_t w = tw[tb[u - 1] + j * js];
 #pragma unroll
             for (int k = 0; k < half; k++) {
-                if (u == 1 && RED_FIRST) ct_bfly_m<MODE, true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+                if ((u == 1 && RED_FIRST) || (MODE == 2 && u == 4)) ct_bfly_m<MODE, true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
                 else ct_bfly_m<MODE, false>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
             }
         }

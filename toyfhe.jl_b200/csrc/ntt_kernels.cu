@@ -17,6 +17,7 @@
 
 int g_ntt_version = 3;  // 1 = one CTA per row (512x32), 2 = persistent 1024x16 + TMA, 3 = persistent 512x32 + TMA (tools/ntt_compare.py)
 bool g_ntt_force_harvey = false;
+int g_ntt_max_mode = 2;
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
 void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
@@ -164,7 +165,7 @@ static int launch_row(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool invers
     if (blocks > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
     if (inverse)
         { ProfScope ps(PC_NTT_INV, st); ntt_inv_row_kernel<R><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_inv, c->d_pp, c->L, s0); }
-    else if (c->ntt_mode == 1 && !g_ntt_force_harvey)
+    else if (c->ntt_mode >= 1 && !g_ntt_force_harvey && g_ntt_max_mode >= 1)
         { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R, 1><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }
     else
         { ProfScope ps(PC_NTT_FWD, st); ntt_fwd_row_kernel<R, 0><<<(unsigned)blocks, Geo::T, smem, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0); }

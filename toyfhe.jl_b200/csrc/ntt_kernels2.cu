@@ -167,7 +167,7 @@ int launch_ntt14(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u3
         ntt_inv14_kernel<<<grid, 1024, ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, s0, (u32)units);
     } else {
         ProfScope ps(PC_NTT_FWD, st);
-        if (c->ntt_mode == 1 && !g_ntt_force_harvey)
+        if (c->ntt_mode >= 1 && !g_ntt_force_harvey && g_ntt_max_mode >= 1)
             ntt_fwd14_kernel<1><<<grid, 1024, ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
         else
             ntt_fwd14_kernel<0><<<grid, 1024, ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
