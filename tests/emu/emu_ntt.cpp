@@ -205,6 +205,27 @@ extern "C" long long emu_ntt3_fwd(u64 q, u64 psi, u32 s0, const u64* in, u64* ou
     }
     return (long long)g_emu_overflow3;
 }
+extern "C" long long emu_ntt3_inv(u64 q, u64 psi, const u64* in, u64* out) {
+    using namespace v3;
+    if ((q >> 60) != 1 || q - (1ull << 60) >= (1ull << 28)) return -1;
+    redent_t tab[16];
+    fill_redtab(tab, q);
+    const Red3 rp = make_red3(q, tab);
+    HostTables ht;
+    build_tables(Geo::N, q, psi, ht);
+    std::vector<tw_t> invc(Geo::N);
+    permute_pass3(ht.inv.data(), invc.data(), 14);
+    std::vector<u64> smem(ROW_WORDS), regs((size_t)Geo::T * 32);
+    g_emu_overflow3 = 0;
+    memcpy(smem.data(), in, Geo::N * 8);   // the flat bulk copy
+    for (u32 t = 0; t < Geo::T; t++) inv_pass3_load(&regs[t * 32], smem.data(), t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass3_compute_store(&regs[t * 32], smem.data(), invc.data(), rp, t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass2(&regs[t * 32], smem.data(), ht.inv.data(), rp, t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass1_load(&regs[t * 32], smem.data(), t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass1_compute_store(&regs[t * 32], out, ht.inv.data(), rp, t, ht.ninv, ht.ninv_w1);
+    return (long long)g_emu_overflow3;
+}
+
 // bank census of the skewed layout: 64-bit accesses per half-warp (passes 1, 2), 128-bit per quarter-warp (pass 3)
 extern "C" int emu_bank_conflicts3() {
     using namespace v3;

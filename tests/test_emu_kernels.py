@@ -154,6 +154,14 @@ def test_v3_forward_kernel(emu, s0):
             got = np.zeros_like(a)
             assert emu.emu_ntt3_fwd(C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got)) == 0
             assert np.array_equal(got, orc.nntt(a))
+            if s0 == 0:
+                emu.emu_ntt3_inv.restype = C.c_longlong
+                back = np.zeros_like(a)
+                assert emu.emu_ntt3_inv(C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
+                assert np.array_equal(back, a)
+                # the inverse must also hold its ranges on arbitrary (not transform-image) canonical input
+                assert emu.emu_ntt3_inv(C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
+                assert np.array_equal(back, orc.inntt(a))
     q40, psi40 = O.prime_chain(1 << 14, (40,))
     assert emu.emu_ntt3_fwd(C.c_uint64(q40[0]), C.c_uint64(psi40[0]), C.c_uint32(0), P(got), P(got)) == -1   # not a 2^60 + e prime
 

@@ -157,4 +157,107 @@ TFB_HD void pass3_compute_store(u64* x, u64* __restrict__ orow, const tw_t* __re
         }
     }
 }
+
+// ------------------------------------------------------------------ inverse (pow2_cyc_rings.jl:308-318)
+// GS butterfly  X' = X + Y, Y' = (X - Y) w.  Products come back in [0,4q) (shoup_lazy4), so every level after the
+// first brings the sum back with the same table: k is estimated from the high words only (it can be one short of
+// floor((X+Y)/2^60), which leaves X' in (0,3q) instead of (0,2q)), and the constant is added inside the 3-input
+// sum.  Inputs of a reducing level are < 4q, of the first level canonical; X - Y + 4q < 8q.
+template <bool RED>
+TFB_HD void gs_bfly3(u64& X, u64& Y, const tw_t w, const Red3& rp) {
+    const u64 x = X, y = Y;
+    const u64 d = x - y + rp.q4;
+#ifndef __CUDA_ARCH__
+    if (y >= rp.q4 || (((u128)x + rp.q4) >> 64) != 0 || (((u128)x + y) >> 64) != 0) g_emu_overflow3++;
+#endif
+    if (RED) {
+        const u32 k = ((u32)(x >> 32) + (u32)(y >> 32)) >> 28;
+        X = x + y + rp.tab[k].c2;
+#ifndef __CUDA_ARCH__
+        if (X >= 3 * rp.q || k > 15) g_emu_overflow3++;
+#endif
+    } else {
+        X = x + y;
+    }
+    Y = shoup_lazy4<28>(d, w.w, w.wp, rp.q, rp.ne);
+}
+// levels LV..FIRST of the inverse ladder; the level executed first reduces iff RED_TOP, all later ones always
+template <int LV, int FIRST, bool RED_TOP>
+TFB_HD void gs_levels3(u64* x, const tw_t* __restrict__ tw, const u32* tb, const Red3& rp, const u32 js = 1) {
+#pragma unroll
+    for (int u = LV; u >= FIRST; u--) {
+        const int half = (1 << LV) >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << (u - 1)); j++) {
+            const tw_t w = tw[tb[u - 1] + j * js];
+#pragma unroll
+            for (int k = 0; k < half; k++) {
+                if (u == LV && !RED_TOP) gs_bfly3<false>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+                else gs_bfly3<true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+            }
+        }
+    }
+}
+// pass 3 (levels 14..11): natural-order canonical input from the flat copy in shared memory
+TFB_HD void inv_pass3_load(u64* x, const u64* smem, const u32 t) {
+    const u32 w = t >> 5, lane = t & 31;
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int c = 0; c < 16; c++) x[g * 16 + c] = smem[(brev_bits((u32)c, R) << 10) | ((2 * w + g) << 5) | lane];
+}
+TFB_HD void inv_pass3_compute_store(u64* x, u64* smem, const tw_t* __restrict__ itwc, const Red3& rp, const u32 t) {
+    const u32 w = t >> 5, lane = t & 31;
+    u64* base = smem + slot(brev_bits(lane, 5), brev_bits(2 * w, 5) * Geo::RS);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        u32 tb[R];
+#pragma unroll
+        for (int u = 1; u <= R; u++) tb[u - 1] = pass3_base<R>(0, (u32)g, u, t);
+        gs_levels3<R, 1, false>(x + g * 16, itwc, tb, rp, Geo::T);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int c = 0; c < 16; c += 2)
+            *reinterpret_cast<ulonglong2*>(base + g * 16 * Geo::RS + c) = make_ulonglong2(x[g * 16 + c], x[g * 16 + c + 1]);
+#else
+        for (int c = 0; c < 16; c++) base[g * 16 * Geo::RS + c] = x[g * 16 + c];
+#endif
+    }
+}
+// pass 2 (levels 10..6)
+TFB_HD void inv_pass2(u64* x, u64* smem, const tw_t* __restrict__ itw, const Red3& rp, const u32 t) {
+    const u32 a2 = t >> R, c2 = t & (Geo::RS - 1);
+    u64* base = smem + slot(a2, c2);
+#pragma unroll
+    for (int b = 0; b < 32; b++) x[b] = base[b * Geo::RS];
+    u32 tb[5];
+#pragma unroll
+    for (int u = 1; u <= 5; u++) tb[u - 1] = (1u << (4 + u)) + (a2 << (u - 1));
+    gs_levels3<5, 1, true>(x, itw, tb, rp);
+#pragma unroll
+    for (int b = 0; b < 32; b++) base[b * Geo::RS] = x[b];
+}
+// pass 1 (levels 5..1, N^-1 folded into level 1: tn = N^-1, twn = N^-1 psi^-brev(1)); canonical natural-order output
+TFB_HD void inv_pass1_load(u64* x, const u64* smem, const u32 t) {
+#pragma unroll
+    for (int a = 0; a < 32; a++) x[a] = smem[slot(a, t)];
+}
+TFB_HD void inv_pass1_compute_store(u64* x, u64* __restrict__ orow, const tw_t* __restrict__ itw, const Red3& rp, const u32 t,
+                                    const tw_t tn, const tw_t twn) {
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = 1u << (s - 1);
+    gs_levels3<5, 2, true>(x, itw, tb, rp);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u64 U = x[k], V = x[k + 16];
+#ifndef __CUDA_ARCH__
+        if (V >= rp.q4 || (((u128)U + V) >> 64) != 0 || (((u128)U + rp.q4) >> 64) != 0) g_emu_overflow3++;
+#endif
+        x[k] = shoup_lazy4<28>(U + V, tn.w, tn.wp, rp.q, rp.ne);
+        x[k + 16] = shoup_lazy4<28>(U - V + rp.q4, twn.w, twn.wp, rp.q, rp.ne);
+    }
+#pragma unroll
+    for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = canon3(x[a], rp);
+}
 }  // namespace v3

@@ -267,6 +267,57 @@ ntt_inv14p_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t*
     }
 }
 
+// third-generation inverse (ntt_core3.cuh), s0 == 0 only
+__global__ void __launch_bounds__(Geo::T, 1)
+ntt_inv14s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                  const PrimeParams* __restrict__ pp, const u32 L, const u32 nunits) {
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    u32 t = threadIdx.x;
+    u32 unit = blockIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+#pragma unroll 1
+    for (u32 i = t; i < L * 16; i += Geo::T) {
+        const u64 q = pp[i >> 4].pc.q;
+        redtab[i].c2 = q - (u64)(i & 15) * q;
+        redtab[i].c3 = redtab[i].c2 + 4 * q;
+    }
+    __syncthreads();
+    if (t == 0 && unit < nunits) {
+        mbar_expect_tx(&bar, ROW_BYTES);
+        tma_load_1d(smem, in + (u64)unit * Geo::N, ROW_BYTES, &bar);
+    }
+    u32 parity = 0;
+    u64 x[32];
+    for (; unit < nunits; unit += gridDim.x) {
+        asm volatile("" : "+r"(t));   // see ntt_fwd14p_kernel
+        const u32 prime = (u32)(unit % L);
+        const tw_t* tw = tw_all + (u64)prime * Geo::N;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, redtab + prime * 16);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        v3::inv_pass3_load(x, smem, t);
+        __syncthreads();  // the flat copy is fully read before it is overwritten in skewed order
+        v3::inv_pass3_compute_store(x, smem, tw_all + (u64)(L + prime) * Geo::N, rp, t);
+        __syncthreads();
+        v3::inv_pass2(x, smem, tw, rp, t);
+        __syncthreads();
+        v3::inv_pass1_load(x, smem, t);
+        __syncthreads();
+        const u32 next = unit + gridDim.x;
+        if (t == 0 && next < nunits) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, ROW_BYTES);
+            tma_load_1d(smem, in + (u64)next * Geo::N, ROW_BYTES, &bar);
+        }
+        v3::inv_pass1_compute_store(x, out + (u64)unit * Geo::N, tw, rp, t, pp[prime].ninv, pp[prime].ninv_w1);
+    }
+}
+
 }  // namespace
 
 int ntt3_setup_device() {
@@ -275,6 +326,7 @@ int ntt3_setup_device() {
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv14p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_inv14s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
     return TFB_OK;
 }
 
@@ -290,7 +342,10 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
     const unsigned grid = (unsigned)(units < (u64)nsm ? units : (u64)nsm);
     if (inverse) {
         ProfScope ps(PC_NTT_INV, st);
-        ntt_inv14p_kernel<<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
+        if (c->ntt_mode == 2 && !g_ntt_force_harvey && g_ntt_max_mode >= 2)
+            ntt_inv14s_kernel<<<grid, Geo::T, v3::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
+        else
+            ntt_inv14p_kernel<<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
     } else {
         ProfScope ps(PC_NTT_FWD, st);
         if (c->ntt_mode == 2 && !g_ntt_force_harvey && g_ntt_max_mode >= 2) {
