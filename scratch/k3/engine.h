@@ -21,7 +21,6 @@ struct tfb_ctx {
     int device;
     u32 N, logN, L;
     int num_sms;
-    bool v3_ok;    // every prime is 2^b + e, 32 <= b <= 60, e < 2^28: third-generation kernels apply (ntt_core3.cuh)
     int ntt_mode;  // 0 = Harvey ladder, 1 = lazy ladder (all primes 2^b + small, 15q < 2^64), 2 = lazy + approximate quotient (all primes 2^60 + e, e < 2^28)
     std::vector<u64> q, psi;
     tw_t* d_fwd;      // [L][N]
@@ -104,9 +103,6 @@ int launch_ntt14(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u3
 // ntt_kernels3.cu
 int ntt3_setup_device();
 int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
-// ntt_kernels4.cu
-int ntt4_setup_device();
-int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
 extern bool g_ntt_force_harvey;
 extern int g_ntt_max_mode;  // debug cap on the ladder mode (2 = no cap)
 extern int g_ntt_version;  // 1 = 512x32 kernels everywhere, 2 = 1024x16 persistent kernels where available

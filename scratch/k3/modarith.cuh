@@ -79,18 +79,20 @@ TFB_D u64 shoup_lazy(u64 x, u64 w, u64 wp, u64 q) {
 }
 TFB_D u64 shoup_lazy(u64 x, tw_t t, u64 q) { return shoup_lazy(x, t.w, t.wp, q); }
 
-// x*w mod q in [0,4q) for primes q = 2^b + e with 32 <= b and e < 2^32 (what the reference's
+// x*w mod q in [0,4q) for primes q = 2^b + e with b >= 32 and e < 2^32 (what the reference's
 // nextprime(2^logq + 1) chains give, crt.jl:282-295); valid for ANY 64-bit x.
 //   quotient: h~ = x1*p1 + hi32(x1*p0) + hi32(x0*p1)  in [h-2, h]  (1 IMAD.WIDE + 2 IMAD.HI instead of the
-//             4 IMAD.WIDE of an exact 64x64 high product; the three products are independent and the
-//             two high words join through one carry chain on the ALU pipe),
+//             4 IMAD.WIDE of an exact 64x64 high product),
 //   tail:     x*w - h~*q = x*w - h~*e - (h~ << b)  (mod 2^64): one IMAD.WIDE less than a generic q.
-// ne = 2^32 - e, shb = b - 32 (a run-time value: one shift and one 3-input add on the ALU pipe; as a
-// compile-time constant ptxas turns it into a multiply on the FMA-heavy pipe, which bounds the kernels).
-// Measured (IMAD.WIDE/IMAD.HI 4 cycles, IMAD 2 cycles per warp instruction, tools/bfly_bench4.cu).
-TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne, u32 shb) {
+// ne = 2^32 - e, SHB = b - 32.  Measured on the FMA-heavy pipe (IMAD.WIDE/IMAD.HI 4 cycles, IMAD 2 cycles
+// per warp instruction, tools/bfly_bench4.cu): 30.8 instead of 34.8 pipe cycles per butterfly.
+#ifndef SL4V
+#define SL4V 0
+#endif
+template <int SHB>
+TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne, u32 shb = SHB) {
 #ifdef __CUDA_ARCH__
-    u32 x0, x1, w0, w1, p0, p1, t0, t1, h0, h1, a, b, lo, hi;
+    u32 x0, x1, w0, w1, p0, p1, h0, h1, a, b, lo, hi;
     u64 t, acc;
     asm("mov.b64 {%0,%1}, %2;" : "=r"(x0), "=r"(x1) : "l"(x));
     asm("mov.b64 {%0,%1}, %2;" : "=r"(w0), "=r"(w1) : "l"(w));
@@ -98,16 +100,28 @@ TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne, u32 shb) {
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x1), "r"(p1));
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(a) : "r"(x1), "r"(p0));
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(b) : "r"(x0), "r"(p1));
-    asm("mov.b64 {%0,%1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-    asm("{\n\t.reg .u32 s;\n\tadd.cc.u32 s, %2, %3;\n\taddc.u32 %1, %5, 0;\n\tadd.cc.u32 %0, s, %4;\n\taddc.u32 %1, %1, 0;\n\t}"
-        : "=r"(h0), "=&r"(h1) : "r"(t0), "r"(a), "r"(b), "r"(t1));
+#if SL4V == 3
+    { u32 t0, t1; asm("mov.b64 {%0,%1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+      asm("{\n\t.reg .u32 s;\n\tadd.cc.u32 s, %2, %3;\n\taddc.u32 %1, %5, 0;\n\tadd.cc.u32 %0, s, %4;\n\taddc.u32 %1, %1, 0;\n\t}" : "=r"(h0), "=&r"(h1) : "r"(t0), "r"(a), "r"(b), "r"(t1)); }
+#else
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(h0), "=r"(h1) : "l"(t + (u64)a + (u64)b));
+#endif
+#if SL4V == 2 || SL4V == 3
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(h0), "r"(ne));
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x0), "r"(w0));
+#else
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(x0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(ne));
+#endif
     asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x0), "r"(w1));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x1), "r"(w0));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(ne));
+#if SL4V == 0
+    hi = hi - h0 - (h0 << SHB);
+#else
     hi = hi - h0 - (h0 << shb);
+#endif
     asm("mov.b64 %0, {%1,%2};" : "=l"(acc) : "r"(lo), "r"(hi));
     return acc;
 #else

@@ -132,7 +132,7 @@ TFB_HD void ct_bfly_m(u64& X, u64& Y, const tw_t w, const RedParams& rp) {
     u64 x = X;
     if (MODE == 2) {
         if (RED) x = reduce_tab(x, rp);
-        const u64 t = shoup_lazy4(Y, w.w, w.wp, rp.q, rp.ne, rp.shb);
+        const u64 t = shoup_lazy4<28>(Y, w.w, w.wp, rp.q, rp.ne);
 #ifndef __CUDA_ARCH__
         if (t >= rp.q4 || x + t < x || (((u128)x + rp.q4 - t) >> 64) != 0) g_emu_overflow++;   // tests/emu: the lazy bounds must hold
 #endif

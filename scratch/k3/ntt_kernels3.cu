@@ -10,7 +10,7 @@
 // definitions); only the data movement differs.
 #include "engine.h"
 #include "ntt_core.cuh"
-#include "ntt_v3_kernels.cuh"
+#include "ntt_core3.cuh"
 
 namespace {
 
@@ -128,6 +128,63 @@ ntt_fwd14p_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t*
     }
 }
 
+// ---- third generation (ntt_core3.cuh): approximate-quotient ladder, fused table reductions, skewed row buffer.
+// The row arrives as 32 bulk copies of 4 KiB (one per block of 512 positions, each to its skewed slot), issued by
+// the 32 lanes of warp 0; everything else follows ntt_fwd14p_kernel.
+__device__ __forceinline__ void tma_load_row_skewed(u64* smem, const u64* src, u64* bar, const u32 lane) {
+    if (lane == 0) mbar_expect_tx(bar, Geo::N * 8);
+    __syncwarp();
+    fence_proxy_async();
+    tma_load_1d(smem + v3::slot(lane, 0), src + lane * Geo::T, Geo::T * 8, bar);
+}
+template <bool S0ZERO>
+__global__ void __launch_bounds__(Geo::T, 1)
+ntt_fwd14s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                  const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits) {
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    const u32 s0 = S0ZERO ? 0 : s0_;
+    u32 t = threadIdx.x;
+    const u64 nrow = (u64)Geo::N << s0;
+    u32 unit = blockIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+#pragma unroll 1
+    for (u32 i = t; i < L * 16; i += Geo::T) {
+        const u64 q = pp[i >> 4].pc.q;
+        redtab[i].c2 = q - (u64)(i & 15) * q;
+        redtab[i].c3 = redtab[i].c2 + 4 * q;
+    }
+    __syncthreads();
+    if (t < 32 && unit < nunits)
+        tma_load_row_skewed(smem, in + (u64)(unit >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N, &bar, t);
+    u32 parity = 0;
+    u64 x[32];
+    for (; unit < nunits; unit += gridDim.x) {
+        const u64 row = unit >> s0;
+        const u32 blk = unit & ((1u << s0) - 1);
+        const u32 prime = (u32)(row % L);
+        const tw_t* tw = tw_all + (u64)prime * nrow;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, redtab + prime * 16);
+        asm volatile("" : "+r"(t));   // see ntt_fwd14p_kernel
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        v3::pass1(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
+        __syncthreads();
+        v3::pass2(x, smem, tw, rp, t, s0, blk);
+        __syncthreads();
+        v3::pass3_load(x, smem, t);
+        __syncthreads();
+        const u32 next = unit + gridDim.x;
+        if (t < 32 && next < nunits)
+            tma_load_row_skewed(smem, in + (u64)(next >> s0) * nrow + (u64)(next & ((1u << s0) - 1)) * Geo::N, &bar, t);
+        v3::pass3_compute_store<S0ZERO>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
+    }
+}
+
 // inverse, s0 == 0 only (for longer rows the natural-order input of a sub-block is strided)
 __global__ void __launch_bounds__(Geo::T, 1)
 ntt_inv14p_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
@@ -210,16 +267,67 @@ ntt_inv14p_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t*
     }
 }
 
+// third-generation inverse (ntt_core3.cuh), s0 == 0 only
+__global__ void __launch_bounds__(Geo::T, 1)
+ntt_inv14s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                  const PrimeParams* __restrict__ pp, const u32 L, const u32 nunits) {
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    u32 t = threadIdx.x;
+    u32 unit = blockIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+#pragma unroll 1
+    for (u32 i = t; i < L * 16; i += Geo::T) {
+        const u64 q = pp[i >> 4].pc.q;
+        redtab[i].c2 = q - (u64)(i & 15) * q;
+        redtab[i].c3 = redtab[i].c2 + 4 * q;
+    }
+    __syncthreads();
+    if (t == 0 && unit < nunits) {
+        mbar_expect_tx(&bar, ROW_BYTES);
+        tma_load_1d(smem, in + (u64)unit * Geo::N, ROW_BYTES, &bar);
+    }
+    u32 parity = 0;
+    u64 x[32];
+    for (; unit < nunits; unit += gridDim.x) {
+        asm volatile("" : "+r"(t));   // see ntt_fwd14p_kernel
+        const u32 prime = (u32)(unit % L);
+        const tw_t* tw = tw_all + (u64)prime * Geo::N;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, redtab + prime * 16);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        v3::inv_pass3_load(x, smem, t);
+        __syncthreads();  // the flat copy is fully read before it is overwritten in skewed order
+        v3::inv_pass3_compute_store(x, smem, tw_all + (u64)(L + prime) * Geo::N, rp, t);
+        __syncthreads();
+        v3::inv_pass2(x, smem, tw, rp, t);
+        __syncthreads();
+        v3::inv_pass1_load(x, smem, t);
+        __syncthreads();
+        const u32 next = unit + gridDim.x;
+        if (t == 0 && next < nunits) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, ROW_BYTES);
+            tma_load_1d(smem, in + (u64)next * Geo::N, ROW_BYTES, &bar);
+        }
+        v3::inv_pass1_compute_store(x, out + (u64)unit * Geo::N, tw, rp, t, pp[prime].ninv, pp[prime].ninv_w1);
+    }
+}
+
 }  // namespace
 
 int ntt3_setup_device() {
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
-    TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_s_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv14p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
-    int rc = v3k::setup_s<4>();
-    if (rc) return rc;
-    return ntt4_setup_device();
+    TFB_CUDA(cudaFuncSetAttribute(ntt_inv14s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::ROW_BYTES));
+    return TFB_OK;
 }
 
 // rows of length 2^(14+s0).  Returns -1 when the persistent kernels do not apply
@@ -234,15 +342,15 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
     const unsigned grid = (unsigned)(units < (u64)nsm ? units : (u64)nsm);
     if (inverse) {
         ProfScope ps(PC_NTT_INV, st);
-        if (c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2)
-            v3k::ntt_inv_s_kernel<4><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
+        if (c->ntt_mode == 2 && !g_ntt_force_harvey && g_ntt_max_mode >= 2)
+            ntt_inv14s_kernel<<<grid, Geo::T, v3::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
         else
             ntt_inv14p_kernel<<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)units);
     } else {
         ProfScope ps(PC_NTT_FWD, st);
-        if (c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2) {
-            if (s0 == 0) v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units);
-            else v3k::ntt_fwd_s_kernel<4, false><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
+        if (c->ntt_mode == 2 && !g_ntt_force_harvey && g_ntt_max_mode >= 2) {
+            if (s0 == 0) ntt_fwd14s_kernel<true><<<grid, Geo::T, v3::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units);
+            else ntt_fwd14s_kernel<false><<<grid, Geo::T, v3::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
         }
         else if (c->ntt_mode >= 1 && !g_ntt_force_harvey && g_ntt_max_mode >= 1)
             ntt_fwd14p_kernel<1><<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);

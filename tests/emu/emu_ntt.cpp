@@ -178,57 +178,77 @@ extern "C" int emu_bank_conflicts2() {
     return worst;
 }
 
-// ---- third-generation forward kernel (ntt_core3.cuh): skewed row buffer, approximate quotient, fused reductions.
-// Returns the number of lazy-range violations (must be 0).
-extern "C" long long emu_ntt3_fwd(u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+// ---- third-generation kernels (ntt_core3.cuh): skewed row buffer, approximate quotient, fused reductions.
+// Return the number of lazy-range violations (must be 0), -1 if the prime is not eligible.
+static u32 floor_log2(u64 q) { u32 b = 0; while (b < 63 && (q >> (b + 1))) b++; return b; }
+template <int R>
+static long long emu3_fwd(u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
     using namespace v3;
-    if ((q >> 60) != 1 || q - (1ull << 60) >= (1ull << 28)) return -1;
+    typedef NttGeo<R> Geo;
+    if (!prime_ok(q)) return -1;
     redent_t tab[16];
     fill_redtab(tab, q);
-    const Red3 rp = make_red3(q, tab);
+    const Red3 rp = make_red3(q, floor_log2(q), tab);
     const u64 Nrow = (u64)Geo::N << s0;
     HostTables ht;
     build_tables(Nrow, q, psi, ht);
     std::vector<tw_t> fwdc(Nrow);
-    permute_pass3(ht.fwd.data(), fwdc.data(), 14 + (int)s0);
-    std::vector<u64> smem(ROW_WORDS), regs((size_t)Geo::T * 32);
+    permute_pass3(ht.fwd.data(), fwdc.data(), 10 + R + (int)s0);
+    std::vector<u64> smem(Lay<R>::ROW_WORDS), regs((size_t)Geo::T * 32);
     g_emu_overflow3 = 0;
     for (u32 blk = 0; blk < (1u << s0); blk++) {
-        for (u32 a = 0; a < 32; a++) memcpy(&smem[slot(a, 0)], in + (u64)blk * Geo::N + a * Geo::T, Geo::T * 8);   // the 32 bulk copies
-        for (u32 t = 0; t < Geo::T; t++) pass1(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
-        for (u32 t = 0; t < Geo::T; t++) pass2(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
-        for (u32 t = 0; t < Geo::T; t++) pass3_load(&regs[t * 32], smem.data(), t);
+        for (u32 a = 0; a < 32; a++) memcpy(&smem[slot<R>(a, 0)], in + (u64)blk * Geo::N + a * Geo::T, Geo::T * 8);   // the 32 bulk copies
+        for (u32 t = 0; t < Geo::T; t++) pass1<R>(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
+        for (u32 t = 0; t < Geo::T; t++) pass2<R>(&regs[t * 32], smem.data(), ht.fwd.data(), rp, t, s0, blk);
+        for (u32 t = 0; t < Geo::T; t++) pass3_load<R>(&regs[t * 32], smem.data(), t);
         for (u32 t = 0; t < Geo::T; t++) {
-            if (s0 == 0) pass3_compute_store<true>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
-            else pass3_compute_store<false>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
+            if (s0 == 0) pass3_compute_store<R, true>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
+            else pass3_compute_store<R, false>(&regs[t * 32], out, fwdc.data(), rp, t, s0, blk);
         }
     }
     return (long long)g_emu_overflow3;
 }
-extern "C" long long emu_ntt3_inv(u64 q, u64 psi, const u64* in, u64* out) {
+template <int R>
+static long long emu3_inv(u64 q, u64 psi, const u64* in, u64* out) {
     using namespace v3;
-    if ((q >> 60) != 1 || q - (1ull << 60) >= (1ull << 28)) return -1;
+    typedef NttGeo<R> Geo;
+    if (!prime_ok(q)) return -1;
     redent_t tab[16];
     fill_redtab(tab, q);
-    const Red3 rp = make_red3(q, tab);
+    const Red3 rp = make_red3(q, floor_log2(q), tab);
     HostTables ht;
     build_tables(Geo::N, q, psi, ht);
     std::vector<tw_t> invc(Geo::N);
-    permute_pass3(ht.inv.data(), invc.data(), 14);
-    std::vector<u64> smem(ROW_WORDS), regs((size_t)Geo::T * 32);
+    permute_pass3(ht.inv.data(), invc.data(), 10 + R);
+    std::vector<u64> smem(Lay<R>::ROW_WORDS), regs((size_t)Geo::T * 32);
     g_emu_overflow3 = 0;
     memcpy(smem.data(), in, Geo::N * 8);   // the flat bulk copy
-    for (u32 t = 0; t < Geo::T; t++) inv_pass3_load(&regs[t * 32], smem.data(), t);
-    for (u32 t = 0; t < Geo::T; t++) inv_pass3_compute_store(&regs[t * 32], smem.data(), invc.data(), rp, t);
-    for (u32 t = 0; t < Geo::T; t++) inv_pass2(&regs[t * 32], smem.data(), ht.inv.data(), rp, t);
-    for (u32 t = 0; t < Geo::T; t++) inv_pass1_load(&regs[t * 32], smem.data(), t);
-    for (u32 t = 0; t < Geo::T; t++) inv_pass1_compute_store(&regs[t * 32], out, ht.inv.data(), rp, t, ht.ninv, ht.ninv_w1);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass3_load<R>(&regs[t * 32], smem.data(), t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass3_compute_store<R>(&regs[t * 32], smem.data(), invc.data(), rp, t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass2<R>(&regs[t * 32], smem.data(), ht.inv.data(), rp, t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass1_load<R>(&regs[t * 32], smem.data(), t);
+    for (u32 t = 0; t < Geo::T; t++) inv_pass1_compute_store<R>(&regs[t * 32], out, ht.inv.data(), rp, t, ht.ninv, ht.ninv_w1);
     return (long long)g_emu_overflow3;
+}
+extern "C" long long emu_ntt3_fwd(int R, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
+    if (R == 4) return emu3_fwd<4>(q, psi, s0, in, out);
+    if (s0 != 0) return -2;
+    if (R == 3) return emu3_fwd<3>(q, psi, 0, in, out);
+    if (R == 2) return emu3_fwd<2>(q, psi, 0, in, out);
+    return -2;
+}
+extern "C" long long emu_ntt3_inv(int R, u64 q, u64 psi, const u64* in, u64* out) {
+    if (R == 4) return emu3_inv<4>(q, psi, in, out);
+    if (R == 3) return emu3_inv<3>(q, psi, in, out);
+    if (R == 2) return emu3_inv<2>(q, psi, in, out);
+    return -2;
 }
 
 // bank census of the skewed layout: 64-bit accesses per half-warp (passes 1, 2), 128-bit per quarter-warp (pass 3)
-extern "C" int emu_bank_conflicts3() {
+template <int R>
+static int bank3() {
     using namespace v3;
+    typedef NttGeo<R> Geo;
     int worst = 1;
     for (u32 wbase = 0; wbase < Geo::T; wbase += 32) {
         for (u32 r = 0; r < 32; r++)
@@ -236,19 +256,32 @@ extern "C" int emu_bank_conflicts3() {
                 int c1[16] = {0}, c2[16] = {0};
                 for (int l = 0; l < 16; l++) {
                     const u32 t = wbase + h * 16 + l;
-                    c1[slot(r, t) % 16]++;
-                    c2[slot(t >> 4, r * 16 + (t & 15)) % 16]++;
+                    c1[slot<R>(r, t) % 16]++;
+                    c2[slot<R>(t >> R, r * Geo::RS + (t & (Geo::RS - 1))) % 16]++;
                 }
                 for (int i = 0; i < 16; i++) { worst = c1[i] > worst ? c1[i] : worst; worst = c2[i] > worst ? c2[i] : worst; }
             }
         const u32 w = wbase >> 5;
-        for (u32 g = 0; g < 2; g++)
-            for (u32 c = 0; c < 16; c += 2)
+        for (u32 g = 0; g < Geo::G; g++)
+            for (u32 c = 0; c < Geo::RS; c += 2)
                 for (int qw = 0; qw < 4; qw++) {
                     int cnt[8] = {0};
-                    for (int l = 0; l < 8; l++) cnt[(slot(brev_bits(qw * 8 + l, 5), brev_bits(2 * w + g, 5) * 16 + c) / 2) % 8]++;
+                    for (int l = 0; l < 8; l++) {
+                        const u32 s = slot<R>(brev_bits(qw * 8 + l, 5), brev_bits(Geo::G * w + g, 5) * Geo::RS + c);
+                        if (s % 2 || s + 1 >= Lay<R>::ROW_WORDS) return 99;   // 128-bit alignment / buffer bound
+                        cnt[(s / 2) % 8]++;
+                    }
                     for (int i = 0; i < 8; i++) worst = cnt[i] > worst ? cnt[i] : worst;
                 }
     }
+    // every position maps to its own slot inside the buffer
+    std::vector<char> seen(Lay<R>::ROW_WORDS, 0);
+    for (u32 a = 0; a < 32; a++)
+        for (u32 i = 0; i < Geo::T; i++) {
+            const u32 s = slot<R>(a, i);
+            if (s >= Lay<R>::ROW_WORDS || seen[s]) return 98;
+            seen[s] = 1;
+        }
     return worst;
 }
+extern "C" int emu_bank_conflicts3(int R) { return R == 4 ? bank3<4>() : R == 3 ? bank3<3>() : R == 2 ? bank3<2>() : -1; }

@@ -152,18 +152,45 @@ def test_v3_forward_kernel(emu, s0):
             a = np.ascontiguousarray(a.reshape(1, N))
             staged = np.ascontiguousarray(fwd_global_stages(a[0], q, psi, s0)).reshape(1, N) if s0 else a
             got = np.zeros_like(a)
-            assert emu.emu_ntt3_fwd(C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got)) == 0
+            assert emu.emu_ntt3_fwd(4, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got)) == 0
             assert np.array_equal(got, orc.nntt(a))
             if s0 == 0:
                 emu.emu_ntt3_inv.restype = C.c_longlong
                 back = np.zeros_like(a)
-                assert emu.emu_ntt3_inv(C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
+                assert emu.emu_ntt3_inv(4, C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
                 assert np.array_equal(back, a)
                 # the inverse must also hold its ranges on arbitrary (not transform-image) canonical input
-                assert emu.emu_ntt3_inv(C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
+                assert emu.emu_ntt3_inv(4, C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
                 assert np.array_equal(back, orc.inntt(a))
-    q40, psi40 = O.prime_chain(1 << 14, (40,))
-    assert emu.emu_ntt3_fwd(C.c_uint64(q40[0]), C.c_uint64(psi40[0]), C.c_uint32(0), P(got), P(got)) == -1   # not a 2^60 + e prime
+    bad = (1 << 60) + (1 << 28) + 1    # e too large for the approximate-quotient tail: rejected before any arithmetic
+    assert emu.emu_ntt3_fwd(4, C.c_uint64(bad), C.c_uint64(3), C.c_uint32(0), P(got), P(got)) == -1
+
+
+@pytest.mark.parametrize("R", [2, 3, 4])
+@pytest.mark.parametrize("logq", [32, 40, 50, 60])
+def test_v3_kernels_all_sizes_and_prime_widths(emu, R, logq):
+    """the same ladder at N = 2^12, 2^13, 2^14 on primes 2^b + e of every width the reference's chains use
+    (60/40-bit CKKS chains of examples/encrypted_mnist, 50-bit primes of test/bfv_crt.jl): forward and inverse
+    bit-exact against the oracle, lazy ranges held on random and extreme rows"""
+    N = 1 << (10 + R)
+    emu.emu_ntt3_fwd.restype = C.c_longlong
+    emu.emu_ntt3_inv.restype = C.c_longlong
+    qs, psis = O.prime_chain(N, (logq,) * 3)
+    for i in (0, 2):
+        q, psi = qs[i], psis[i]
+        orc = CO.Rns(N, [q], [psi])
+        rng = np.random.default_rng(R * 100 + logq + i)
+        rows = [rng.integers(0, q, size=N, dtype=np.uint64), np.full(N, q - 1, dtype=np.uint64),
+                np.where(np.arange(N) % 2 == 0, q - 1, 0).astype(np.uint64)]
+        for a in rows:
+            a = np.ascontiguousarray(a.reshape(1, N))
+            got, back = np.zeros_like(a), np.zeros_like(a)
+            assert emu.emu_ntt3_fwd(R, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(a), P(got)) == 0
+            assert np.array_equal(got, orc.nntt(a))
+            assert emu.emu_ntt3_inv(R, C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
+            assert np.array_equal(back, a)
+            assert emu.emu_ntt3_inv(R, C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
+            assert np.array_equal(back, orc.inntt(a))
 
 
 def test_worst_case_inputs_lazy_bounds(emu):
@@ -204,4 +231,5 @@ def test_long_rows_as_sub_blocks(emu, s0, gen):
 def test_shared_memory_layouts_are_conflict_free(emu):
     assert emu.emu_bank_conflicts(4) == 1      # 512x32 kernel at N = 2^14
     assert emu.emu_bank_conflicts2() == 1      # 1024x16 kernel
-    assert emu.emu_bank_conflicts3() == 1      # skewed layout of the third-generation forward kernel
+    for R in (2, 3, 4):                        # skewed layout of the third-generation kernels
+        assert emu.emu_bank_conflicts3(R) == 1

@@ -310,12 +310,14 @@ def test_error_paths():
 
 # ------------------------------------------------ kernel variants must all agree
 @pytest.mark.parametrize("version,mode", [(1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)])
-@pytest.mark.parametrize("logN,logqs", [(14, [60] * 8), (14, [60, 40, 40]), (15, [60, 60]), (16, [60]), (13, [60, 40])])
+@pytest.mark.parametrize("logN,logqs", [(14, [60] * 8), (14, [60, 40, 40]), (15, [60, 60]), (16, [60]), (13, [60, 40]),
+                                        (13, [60, 40, 40, 40, 40, 40, 60]), (12, [50, 50, 32]), (15, [60, 40, 40])])
 def test_ntt_kernel_variants(version, mode, logN, logqs):
     N = 1 << logN
     qs, psis, ctx, orc = _ring(N, logqs)
     rng = np.random.default_rng(logN + version)
-    B = 40 if logN == 14 else 3           # > 148 rows: persistent CTAs loop over several rows
+    # more rows than resident CTAs: the persistent kernels loop over several rows
+    B = {14: 40, 13: 100, 12: 250}.get(logN, 3) if len(logqs) != 7 else 45
     a = _rand(rng, N, qs, (B,))
     a[0, 0, :] = qs[0] - 1                # worst case for the lazy ranges
     want = orc.nntt(a)

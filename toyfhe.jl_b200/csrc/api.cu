@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "ntt_core3.cuh"
 #include "tables.h"
 
 static thread_local std::string g_err;
@@ -227,6 +228,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->conv_ok = false;
     c->num_sms = 0;
     c->ntt_mode = 1;
+    c->v3_ok = true;
     bool all60 = true;
     // [0, L*N): natural psi^brev(k) tables; [L*N, 2*L*N): thread-order copies for pass 3 (tables.h permute_pass3)
     std::vector<tw_t> fwd((size_t)2 * L * N), inv((size_t)2 * L * N);
@@ -248,6 +250,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         const bool lazy_ok = (e <= ((1ull << sh) >> 4)) && ((u128)q[i] * 15 < ((u128)1 << 64));
         if (!lazy_ok) c->ntt_mode = 0;
         if (sh != 60 || e >= (1ull << 28)) all60 = false;
+        if (!lazy_ok || !v3::prime_ok(q[i])) c->v3_ok = false;
     }
     if (c->ntt_mode == 1 && all60) c->ntt_mode = 2;   // approximate-quotient ladder (ntt_core.cuh MODE 2)
     int rc = TFB_OK;

@@ -217,6 +217,10 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     }
     if (logN == 14 && g_ntt_version == 2) return launch_ntt14(c, in, out, rows, inverse, 0, st);
     if (logN == 14 && g_ntt_version == 3) return launch_ntt14p(c, in, out, rows, inverse, 0, st);
+    if ((logN == 12 || logN == 13) && g_ntt_version == 3) {
+        const int rc = launch_ntt_s(c, in, out, rows, inverse, st);
+        if (rc != -1) return rc;
+    }
     if (logN <= 14) return launch_row_dispatch(c, (int)logN - 10, in, out, rows, inverse, 0, st);
     if (logN > 16) { tfb_set_error("N > 2^16 is not supported"); return TFB_EUNSUPPORTED; }
     // long rows: s0 global levels + row-resident sub-blocks, through scratch

@@ -1,0 +1,19 @@
+// Third-generation persistent row kernels (ntt_v3_kernels.cuh) for N = 2^12 and 2^13 -- the ring degrees of the
+// reference's BFV tests (test/bfv_crt.jl: 2048..4096) and of examples/encrypted_mnist (N = 2^13, 60/40-bit chain).
+// Two (N = 2^13) or four (N = 2^12) CTAs are resident per SM.  Same arithmetic and index maps as the N = 2^14
+// instantiation in ntt_kernels3.cu; this translation unit exists so the instantiations compile in parallel.
+#include "ntt_v3_kernels.cuh"
+
+int ntt4_setup_device() {
+    int rc = v3k::setup_s<2>();
+    if (rc) return rc;
+    return v3k::setup_s<3>();
+}
+
+// Returns -1 when the third-generation kernels do not apply (the caller falls back to ntt_kernels.cu).
+int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st) {
+    if (!c->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2) return -1;
+    if (c->logN == 12) return v3k::launch_s<2>(c, in, out, rows, inverse, st);
+    if (c->logN == 13) return v3k::launch_s<3>(c, in, out, rows, inverse, st);
+    return -1;
+}

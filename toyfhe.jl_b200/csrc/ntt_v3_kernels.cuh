@@ -1,0 +1,179 @@
+// Persistent row kernels of the third-generation ladder (ntt_core3.cuh), N = 2^(10+R) sub-blocks, R = 2..4.
+//   * CTAs of T = N/32 threads walk over their rows with stride gridDim.x; 512/T CTAs are resident per SM
+//     (one at N = 2^14, two at 2^13, four at 2^12), so that at the smaller sizes the shared-memory phases of
+//     one row overlap the butterflies of another;
+//   * the next row arrives as 32 bulk copies (cp.async.bulk, TMA, SASS UBLKCP) issued by the lanes of warp 0
+//     as soon as the current row's last shared-memory reads are done, each to its skewed slot;
+//   * the per-prime reduction tables (16 entries of 16 bytes) are built once per CTA in shared memory.
+// Included by ntt_kernels3.cu (R = 4) and ntt_kernels4.cu (R = 2, 3) so the instantiations compile in parallel.
+#pragma once
+#include "engine.h"
+#include "ntt_core3.cuh"
+
+namespace v3k {
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_V3K:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_V3K;\n\t"
+        "bra WAIT_LOOP_V3K;\n\t"
+        "DONE_V3K:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// one row of N positions as 32 bulk copies of T words, copy a to its skewed slot
+template <int R>
+__device__ __forceinline__ void tma_load_row_skewed(u64* smem, const u64* src, u64* bar, const u32 lane) {
+    typedef NttGeo<R> Geo;
+    if (lane == 0) mbar_expect_tx(bar, Geo::N * 8);
+    __syncwarp();
+    fence_proxy_async();
+    tma_load_1d(smem + v3::slot<R>(lane, 0), src + lane * Geo::T, Geo::T * 8, bar);
+}
+__device__ __forceinline__ void build_redtab(v3::redent_t* redtab, const PrimeParams* __restrict__ pp, const u32 L, const u32 t,
+                                             const u32 nthreads) {
+#pragma unroll 1
+    for (u32 i = t; i < L * 16; i += nthreads) {
+        const u64 q = pp[i >> 4].pc.q;
+        redtab[i].c2 = q - (u64)(i & 15) * q;
+        redtab[i].c3 = redtab[i].c2 + 4 * q;
+    }
+}
+
+template <int R, bool S0ZERO>
+__global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
+ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    const u32 s0 = S0ZERO ? 0 : s0_;
+    u32 t = threadIdx.x;
+    const u64 nrow = (u64)Geo::N << s0;
+    u32 unit = blockIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    build_redtab(redtab, pp, L, t, Geo::T);
+    __syncthreads();
+    if (t < 32 && unit < nunits)
+        tma_load_row_skewed<R>(smem, in + (u64)(unit >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N, &bar, t);
+    u32 parity = 0;
+    u64 x[32];
+    for (; unit < nunits; unit += gridDim.x) {
+        const u64 row = unit >> s0;
+        const u32 blk = unit & ((1u << s0) - 1);
+        const u32 prime = (u32)(row % L);
+        const tw_t* tw = tw_all + (u64)prime * nrow;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        // opaque to the optimiser: keeps the per-row address arithmetic inside the loop (hoisted, it
+        // is 32 loop-invariant values per thread that ptxas spills to local memory)
+        asm volatile("" : "+r"(t));
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
+        __syncthreads();
+        v3::pass2<R>(x, smem, tw, rp, t, s0, blk);
+        __syncthreads();
+        v3::pass3_load<R>(x, smem, t);
+        __syncthreads();
+        const u32 next = unit + gridDim.x;
+        if (t < 32 && next < nunits)
+            tma_load_row_skewed<R>(smem, in + (u64)(next >> s0) * nrow + (u64)(next & ((1u << s0) - 1)) * Geo::N, &bar, t);
+        v3::pass3_compute_store<R, S0ZERO>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
+    }
+}
+
+// inverse, s0 == 0 only (for longer rows the natural-order input of a sub-block is strided)
+template <int R>
+__global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
+ntt_inv_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 nunits) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    u32 t = threadIdx.x;
+    u32 unit = blockIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    build_redtab(redtab, pp, L, t, Geo::T);
+    __syncthreads();
+    if (t == 0 && unit < nunits) {
+        mbar_expect_tx(&bar, Geo::N * 8);
+        tma_load_1d(smem, in + (u64)unit * Geo::N, Geo::N * 8, &bar);
+    }
+    u32 parity = 0;
+    u64 x[32];
+    for (; unit < nunits; unit += gridDim.x) {
+        asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
+        const u32 prime = (u32)(unit % L);
+        const tw_t* tw = tw_all + (u64)prime * Geo::N;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        v3::inv_pass3_load<R>(x, smem, t);
+        __syncthreads();  // the flat copy is fully read before it is overwritten in skewed order
+        v3::inv_pass3_compute_store<R>(x, smem, tw_all + (u64)(L + prime) * Geo::N, rp, t);
+        __syncthreads();
+        v3::inv_pass2<R>(x, smem, tw, rp, t);
+        __syncthreads();
+        v3::inv_pass1_load<R>(x, smem, t);
+        __syncthreads();
+        const u32 next = unit + gridDim.x;
+        if (t == 0 && next < nunits) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, Geo::N * 8);
+            tma_load_1d(smem, in + (u64)next * Geo::N, Geo::N * 8, &bar);
+        }
+        v3::inv_pass1_compute_store<R>(x, out + (u64)unit * Geo::N, tw, rp, t, pp[prime].ninv, pp[prime].ninv_w1);
+    }
+}
+
+template <int R>
+int setup_s() {
+    const int smem = (int)v3::Lay<R>::ROW_BYTES;
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_inv_s_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return TFB_OK;
+}
+// rows of exactly N = 2^(10+R) positions
+template <int R>
+int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st) {
+    typedef NttGeo<R> Geo;
+    if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+    const u64 slots = (u64)(c->num_sms > 0 ? c->num_sms : 148) * (512 / Geo::T);
+    const unsigned grid = (unsigned)(rows < slots ? rows : slots);
+    if (inverse) {
+        ProfScope ps(PC_NTT_INV, st);
+        ntt_inv_s_kernel<R><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)rows);
+    } else {
+        ProfScope ps(PC_NTT_FWD, st);
+        ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows);
+    }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+}  // namespace v3k
