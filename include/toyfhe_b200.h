@@ -67,6 +67,11 @@ int tfb_debug_ntt_force_harvey(int on);
 /* testing hook: cap the forward-ladder range policy (0 = Harvey, 1 = lazy, 2 = lazy + approximate quotient,
  * the default when every prime is 2^60 + e with e < 2^28); all must agree bit for bit */
 int tfb_debug_ntt_max_mode(int m);
+/* kernel selection hook for N = 2^15 / 2^16: 1 = hold a row as a pair of 2^14 sub-blocks in a thread-block cluster of
+ * two CTAs and run the coupling level through distributed shared memory (ntt_kernels5.cu); 0 (default) = global
+ * passes for the coupling levels.  Measured equal (forward) or slower (inverse) on B200 -- DSMEM moves ~20 B/clk/SM,
+ * the same as one SM's share of HBM -- so it is kept as a checked alternative only; both must agree bit for bit. */
+int tfb_debug_ntt_pair(int on);
 
 /* ---- ring construction helpers (host only, no GPU needed) ---------------- */
 /* NegacyclicRing(N, logqs) prime chain, crt.jl:282-295: ascending-logq order,

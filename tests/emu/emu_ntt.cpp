@@ -244,6 +244,77 @@ extern "C" long long emu_ntt3_inv(int R, u64 q, u64 psi, const u64* in, u64* out
     return -2;
 }
 
+// rows of 2^15 as a pair of sub-blocks (cluster of two CTAs exchanging through distributed shared memory)
+extern "C" long long emu_ntt3_pair_fwd(u64 q, u64 psi, const u64* in, u64* out) {
+    using namespace v3;
+    constexpr int R = 4;
+    typedef NttGeo<R> Geo;
+    if (!prime_ok(q)) return -1;
+    redent_t tab[16];
+    fill_redtab(tab, q);
+    const Red3 rp = make_red3(q, floor_log2(q), tab);
+    const u64 Nrow = (u64)Geo::N * 2;
+    HostTables ht;
+    build_tables(Nrow, q, psi, ht);
+    std::vector<tw_t> fwdc(Nrow);
+    permute_pass3(ht.fwd.data(), fwdc.data(), 15);
+    std::vector<u64> smem[2], regs[2];
+    g_emu_overflow3 = 0;
+    for (u32 r = 0; r < 2; r++) {
+        smem[r].assign(Lay<R>::ROW_WORDS, 0);
+        regs[r].assign((size_t)Geo::T * 32, 0);
+        for (u32 a = 0; a < 32; a++) memcpy(&smem[r][slot<R>(a, 0)], in + (u64)r * Geo::N + a * Geo::T, Geo::T * 8);
+    }
+    for (u32 r = 0; r < 2; r++)
+        for (u32 t = 0; t < Geo::T; t++) {
+            pass1_cross_load<R>(&regs[r][t * 32], smem[r].data(), smem[1 - r].data(), r, ht.fwd[1], rp, t);
+            pass1_cross_levels(&regs[r][t * 32], ht.fwd.data(), rp, 1, r);
+        }
+    for (u32 r = 0; r < 2; r++) {
+        for (u32 t = 0; t < Geo::T; t++) pass1_store<R>(&regs[r][t * 32], smem[r].data(), t);
+        for (u32 t = 0; t < Geo::T; t++) pass2<R>(&regs[r][t * 32], smem[r].data(), ht.fwd.data(), rp, t, 1, r);
+        for (u32 t = 0; t < Geo::T; t++) pass3_load<R>(&regs[r][t * 32], smem[r].data(), t);
+        for (u32 t = 0; t < Geo::T; t++) pass3_compute_store<R, false>(&regs[r][t * 32], out, fwdc.data(), rp, t, 1, r);
+    }
+    return (long long)g_emu_overflow3;
+}
+extern "C" long long emu_ntt3_pair_inv(u64 q, u64 psi, const u64* in, u64* out) {
+    using namespace v3;
+    constexpr int R = 4;
+    typedef NttGeo<R> Geo;
+    if (!prime_ok(q)) return -1;
+    redent_t tab[16];
+    fill_redtab(tab, q);
+    const Red3 rp = make_red3(q, floor_log2(q), tab);
+    const u64 Nrow = (u64)Geo::N * 2;
+    HostTables ht;
+    build_tables(Nrow, q, psi, ht);
+    std::vector<tw_t> invc(Nrow);
+    permute_pass3(ht.inv.data(), invc.data(), 15);
+    std::vector<u64> smem[2], regs[2];
+    g_emu_overflow3 = 0;
+    for (u32 r = 0; r < 2; r++) {
+        smem[r].assign(Lay<R>::ROW_WORDS, 0);
+        regs[r].assign((size_t)Geo::T * 32, 0);
+        memcpy(smem[r].data(), in + (u64)r * Geo::N, Geo::N * 8);   // one contiguous half each
+    }
+    for (u32 r = 0; r < 2; r++)
+        for (u32 t = 0; t < Geo::T; t++) inv_pass3_load_pair<R>(&regs[r][t * 32], smem[r].data(), smem[1 - r].data(), r, t);
+    for (u32 r = 0; r < 2; r++) {
+        for (u32 t = 0; t < Geo::T; t++) inv_pass3_compute_store<R>(&regs[r][t * 32], smem[r].data(), invc.data(), rp, t, r);
+        for (u32 t = 0; t < Geo::T; t++) inv_pass2<R>(&regs[r][t * 32], smem[r].data(), ht.inv.data(), rp, t, 1, r);
+        for (u32 t = 0; t < Geo::T; t++) inv_pass1_load<R>(&regs[r][t * 32], smem[r].data(), t);
+        for (u32 t = 0; t < Geo::T; t++) inv_pass1_levels_all(&regs[r][t * 32], ht.inv.data(), rp, 1, r);
+        for (u32 t = 0; t < Geo::T; t++) pass1_store<R>(&regs[r][t * 32], smem[r].data(), t);
+    }
+    for (u32 r = 0; r < 2; r++)
+        for (u32 t = 0; t < Geo::T; t++) {
+            inv_cross_combine<R>(&regs[r][t * 32], smem[1 - r].data(), r, rp, t);
+            inv_cross_finish<R>(&regs[r][t * 32], out + (u64)r * Geo::N, r ? ht.ninv_w1 : ht.ninv, rp, t);
+        }
+    return (long long)g_emu_overflow3;
+}
+
 // bank census of the skewed layout: 64-bit accesses per half-warp (passes 1, 2), 128-bit per quarter-warp (pass 3)
 template <int R>
 static int bank3() {

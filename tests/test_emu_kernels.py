@@ -193,6 +193,30 @@ def test_v3_kernels_all_sizes_and_prime_widths(emu, R, logq):
             assert np.array_equal(back, orc.inntt(a))
 
 
+@pytest.mark.parametrize("logq", [60, 40])
+def test_v3_pair_kernels_for_rows_of_2_to_15(emu, logq):
+    """N = 2^15 (CKKS config of BASELINE.json) as a pair of sub-blocks: the cross level of the forward transform
+    runs first on the pair, of the inverse last (N^-1 folded in); bit-exact, lazy ranges held"""
+    N = 1 << 15
+    emu.emu_ntt3_pair_fwd.restype = C.c_longlong
+    emu.emu_ntt3_pair_inv.restype = C.c_longlong
+    qs, psis = O.prime_chain(N, (logq,) * 2)
+    q, psi = qs[1], psis[1]
+    orc = CO.Rns(N, [q], [psi])
+    rng = np.random.default_rng(logq)
+    rows = [rng.integers(0, q, size=N, dtype=np.uint64), np.full(N, q - 1, dtype=np.uint64),
+            np.where(np.arange(N) < N // 2, q - 1, 0).astype(np.uint64), np.where(np.arange(N) % 2 == 0, q - 1, 1).astype(np.uint64)]
+    for a in rows:
+        a = np.ascontiguousarray(a.reshape(1, N))
+        got, back = np.zeros_like(a), np.zeros_like(a)
+        assert emu.emu_ntt3_pair_fwd(C.c_uint64(q), C.c_uint64(psi), P(a), P(got)) == 0
+        assert np.array_equal(got, orc.nntt(a))
+        assert emu.emu_ntt3_pair_inv(C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
+        assert np.array_equal(back, a)
+        assert emu.emu_ntt3_pair_inv(C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
+        assert np.array_equal(back, orc.inntt(a))
+
+
 def test_worst_case_inputs_lazy_bounds(emu):
     """all-(q-1) rows maximise every lazy intermediate: the lazy ladder must not wrap 2^64"""
     N = 1 << 14

@@ -1,6 +1,7 @@
 // C-ABI of libtoyfhe_b200.so (see include/toyfhe_b200.h for the contract and the
 // reference methods each entry point replaces).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -120,6 +121,11 @@ int tfb_debug_ntt_version(int v) {
 }
 int tfb_debug_ntt_max_mode(int m) {
     g_ntt_max_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
+    return TFB_OK;
+}
+int tfb_debug_ntt_pair(int on) {
+    extern bool g_ntt_pair;
+    g_ntt_pair = on != 0;
     return TFB_OK;
 }
 int tfb_debug_ntt_force_harvey(int on) {
@@ -266,6 +272,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     if (!rc) rc = ntt_setup_device();
     if (!rc) rc = ntt2_setup_device();
     if (!rc) rc = ntt3_setup_device();
+    if (!rc) rc = ntt5_setup_device();
     if (!rc) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
@@ -724,7 +731,12 @@ int tfb_bfv_mul_host(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, c
     cudaStream_t st = (cudaStream_t)stream;
     const size_t poly = (size_t)cq->L * cq->N;
     // chunk: about 32 MiB of input per copy, at least one pair
-    u64 ch = (u64)((size_t)(32u << 20) / (4 * poly * sizeof(u64)));
+    static const size_t chunk_bytes = [] {   // TFB_HOST_CHUNK_MIB: input bytes per pipelined copy (tuning knob, default 32 MiB)
+        const char* e = getenv("TFB_HOST_CHUNK_MIB");
+        const long v = e ? atol(e) : 0;
+        return (size_t)(v > 0 && v <= 1024 ? v : 32) << 20;
+    }();
+    u64 ch = (u64)(chunk_bytes / (4 * poly * sizeof(u64)));
     if (ch < 1) ch = 1;
     if (ch > batch) ch = batch;
     HostPipe* P;

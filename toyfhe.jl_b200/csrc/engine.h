@@ -107,6 +107,10 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
 // ntt_kernels4.cu
 int ntt4_setup_device();
 int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
+// ntt_kernels5.cu
+int ntt5_setup_device();
+int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);
+int launch_ntt_pair(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
 extern bool g_ntt_force_harvey;
 extern int g_ntt_max_mode;  // debug cap on the ladder mode (2 = no cap)
 extern int g_ntt_version;  // 1 = 512x32 kernels everywhere, 2 = 1024x16 persistent kernels where available

@@ -18,6 +18,7 @@
 int g_ntt_version = 3;  // 1 = one CTA per row (512x32), 2 = persistent 1024x16 + TMA, 3 = persistent 512x32 + TMA (tools/ntt_compare.py)
 bool g_ntt_force_harvey = false;
 int g_ntt_max_mode = 2;
+bool g_ntt_pair = false;  // N > 2^14: cluster-pair kernels (ntt_kernels5.cu) instead of global passes for the coupling level
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
 void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
@@ -232,7 +233,24 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     const u64 total = rows << (logN - 1);
     const unsigned tb = 256;
     const unsigned nb = (unsigned)((total + tb - 1) / tb);
+    const bool pair = g_ntt_pair && g_ntt_version == 3 && c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2;
     if (!inverse) {
+        // cluster-pair kernel (ntt_kernels5.cu): levels 1..s0-1 as global passes, level s0 inside the pair
+        if (pair) {
+            const u64* src = in;
+            for (u32 s = 1; s + 1 <= s0; s++) {
+                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
+                src = tmp;
+            }
+            TFB_CUDA(cudaGetLastError());
+            rc = launch_ntt_pair(c, src, out, rows, false, s0, st);
+            if (rc != -1) return rc;
+            if (s0 > 1) {   // pair kernel unavailable after all: finish the remaining global level
+                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(tmp, tmp, c->d_fwd, c->d_pp, c->L, logN, s0, total); }
+                TFB_CUDA(cudaGetLastError());
+                return launch_ntt14p(c, tmp, out, rows, false, s0, st);
+            }
+        }
         const u64* src = in;
         for (u32 s = 1; s <= s0; s++) {
             { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
@@ -243,7 +261,12 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
         if (g_ntt_version == 3) return launch_ntt14p(c, tmp, out, rows, false, s0, st);
         return launch_row_dispatch(c, 4, tmp, out, rows, false, s0, st);
     }
-    rc = g_ntt_version == 2 ? launch_ntt14(c, in, tmp, rows, true, s0, st) : launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
+    if (pair && s0 == 1) {
+        rc = launch_ntt_pair(c, in, out, rows, true, 1, st);
+        if (rc != -1) return rc;
+    }
+    rc = g_ntt_version == 3 ? launch_ntt_inv_sub(c, in, tmp, rows, s0, st) : -1;
+    if (rc == -1) rc = g_ntt_version == 2 ? launch_ntt14(c, in, tmp, rows, true, s0, st) : launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
     if (rc) return rc;
     for (u32 s = s0; s >= 1; s--) {
         { ProfScope ps(PC_NTT_OTHER, st); ntt_inv_stage_kernel<<<nb, tb, 0, st>>>(tmp, s == 1 ? out : tmp, c->d_inv, c->d_pp, c->L, logN, s, total); }

@@ -151,6 +151,50 @@ ntt_inv_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     }
 }
 
+// inverse over the sub-blocks of longer rows (s0 > 0): sub-block blk's natural-order input is strided
+// (n = (kl << s0) + brev_s0(blk)), so it is read with ordinary loads instead of a bulk copy; the sub-block's 14 levels
+// follow, and its canonical results go to positions blk*N .. of the row for the global inverse stages.
+template <int R>
+__global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
+ntt_inv_sub_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                   const PrimeParams* __restrict__ pp, const u32 L, const u32 s0, const u32 nunits) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    u32 t = threadIdx.x;
+    const u64 nrow = (u64)Geo::N << s0;
+    build_redtab(redtab, pp, L, t, Geo::T);
+    __syncthreads();
+    u64 x[32];
+    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
+        const u64 row = unit >> s0;
+        const u32 blk = unit & ((1u << s0) - 1);
+        const u32 prime = (u32)(row % L);
+        const tw_t* tw = tw_all + (u64)prime * nrow;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        {
+            const u32 w = t >> 5, lane = t & 31;
+            const u64* irow = in + row * nrow + brev_bits(blk, (int)s0);
+#pragma unroll
+            for (int g = 0; g < (int)Geo::G; g++)
+#pragma unroll
+                for (int c = 0; c < (int)Geo::RS; c++)
+                    x[g * Geo::RS + c] = irow[(u64)((brev_bits((u32)c, R) << 10) | ((Geo::G * w + g) << 5) | lane) << s0];
+        }
+        v3::inv_pass3_compute_store<R>(x, smem, tw_all + (u64)(L + prime) * nrow, rp, t, blk);
+        __syncthreads();
+        v3::inv_pass2<R>(x, smem, tw, rp, t, s0, blk);
+        __syncthreads();
+        v3::inv_pass1_load<R>(x, smem, t);
+        __syncthreads();              // the buffer is free for the next unit's pass 3
+        v3::inv_pass1_levels_all(x, tw, rp, s0, blk);
+        u64* orow = out + row * nrow + (u64)blk * Geo::N;
+#pragma unroll
+        for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = v3::canon3(x[a], rp);
+    }
+}
+
 template <int R>
 int setup_s() {
     const int smem = (int)v3::Lay<R>::ROW_BYTES;

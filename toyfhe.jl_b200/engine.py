@@ -22,7 +22,7 @@ _lib = None
 ABI_SYMBOLS = [
     "tfb_last_error", "tfb_version", "tfb_kernel_launches",
     "tfb_profile_enable", "tfb_profile_classes", "tfb_profile_class_name", "tfb_profile_read",
-    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode",
+    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode", "tfb_debug_ntt_pair",
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
@@ -83,6 +83,11 @@ def ntt_force_harvey(on: bool) -> None:
 def ntt_max_mode(m: int) -> None:
     """testing hook: cap the forward ladder's range policy (0 Harvey, 1 lazy, 2 lazy + approximate quotient)"""
     _check(load_library().tfb_debug_ntt_max_mode(C.c_int(int(m))))
+
+
+def ntt_pair(on: bool) -> None:
+    """testing hook: N = 2^15 / 2^16 rows as cluster pairs exchanging through distributed shared memory"""
+    _check(load_library().tfb_debug_ntt_pair(C.c_int(1 if on else 0)))
 
 
 def profile_enable(on: bool) -> None:
