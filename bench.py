@@ -170,6 +170,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     def barrier():

@@ -161,6 +161,16 @@ int tfb_keyswitch_digits(tfb_ctx* ctx, tfb_ctx* ctx_target, uint32_t w, const ui
 int tfb_keyswitch(tfb_ctx* ctx, tfb_ctx* ctx_ext, uint32_t w, const uint64_t* key_dual, uint32_t D,
                   const uint64_t* ct, uint32_t comps, uint64_t* out, uint64_t batch, void* stream);
 
+/* Residue-sharded keyswitch (BASELINE config 4, "residues sharded 2/4/8 GPU"): this rank owns
+ * the primes [first, first + Ls) of ctx, ctx_shard = the ring over exactly those primes.  ct is the whole ciphertext
+ * [batch][comps][L][N] (replicated on every rank): the digit decomposition needs every residue of a coefficient
+ * (rlwe_she.jl:328-337), but each digit polynomial is then transformed and multiplied only under this rank's primes
+ * with this rank's rows of the key, key_dual_shard [D][2][Ls][N] -- per-prime work is independent (crt.jl:250-254).
+ * out_shard [batch][2][Ls][N] = rows first..first+Ls-1 of what tfb_keyswitch returns; the caller assembles the rows
+ * of all ranks with ONE all-gather (toyfhe.jl_b200/sharding.py).  Plain parameters only (no special prime). */
+int tfb_keyswitch_shard(tfb_ctx* ctx, tfb_ctx* ctx_shard, uint32_t first, uint32_t w, const uint64_t* key_dual_shard, uint32_t D,
+                        const uint64_t* ct, uint32_t comps, uint64_t* out_shard, uint64_t batch, void* stream);
+
 /* ---- host-buffer entry points (pinned or pageable host memory) ------------------ */
 /* Same semantics as the device versions; copies in, runs, copies out and
  * synchronises `stream` before returning. */

@@ -65,3 +65,45 @@ def test_sharded_bfv_mul_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), 5, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok.npy")
+
+
+def _ks_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        import toyfhe_b200 as T
+        from toyfhe_b200 import sharding as S
+        N, L, w = 1024, 4, 2
+        qs, psis = T.prime_chain(N, [60] * L)
+        ctx = T.Context(N, qs, psis, device=rank)
+        rng = np.random.default_rng(21)            # replicated ciphertext and key
+
+        def rnd(shape):
+            out = np.empty(shape + (L, N), dtype=np.uint64)
+            for i, q in enumerate(qs):
+                out[..., i, :] = rng.integers(0, q, size=shape + (N,), dtype=np.uint64)
+            return out
+
+        D = T.ndigits(qs, w)
+        key, ct = rnd((D, 2)), rnd((1, 3))
+        key_dual = ctx.ntt_fwd(ctx.to_device(key))
+        d_ct = ctx.to_device(ct)
+        lo, hi = S.shard_range(L, rank, world)
+        shard = T.Context(N, qs[lo:hi], psis[lo:hi], device=rank)
+        krows = S.key_rows_for_shard(key_dual, lo, hi)
+        res = S.keyswitch_residue_sharded(lambda a, b: ctx.keyswitch_shard(shard, a, krows, d_ct, w), L)
+        whole = ctx.keyswitch(key_dual, d_ct, w)
+        assert torch.equal(res, whole)
+        np.save(os.path.join(outdir, f"ks{rank}.npy"), np.array([1]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_residue_sharded_keyswitch_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_ks_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ks0.npy") and os.path.exists(tmp_path / "ks1.npy")

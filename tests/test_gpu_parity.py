@@ -249,6 +249,37 @@ def test_keyswitch_plain(N, logqs, w, comps):
         assert np.array_equal(got[b, 0], w1) and np.array_equal(got[b, 1], w2)
 
 
+@pytest.mark.parametrize("N,logqs,w,comps,world", [(64, [60, 60, 40], 7, 3, 2), (1024, [60] * 4, 2, 3, 4), (64, [50, 50, 50], 0, 2, 3),
+                                                   (2 ** 14, [60] * 8, 2, 3, 8)])
+def test_keyswitch_residue_shards_equal_whole(N, logqs, w, comps, world):
+    """BASELINE config 4 (residues sharded over GPUs): the rows each rank computes with tfb_keyswitch_shard, put
+    together, are exactly tfb_keyswitch's result (and the oracle's at the sizes it finishes quickly)"""
+    from toyfhe_b200 import sharding as S
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(N + w + world)
+    D = ctx.L if w == 0 else T.ndigits(qs, w)
+    key = _rand(rng, N, qs, (D, 2))
+    B = 2 if N < 2 ** 14 else 1
+    ct = _rand(rng, N, qs, (B, comps))
+    key_dual = ctx.ntt_fwd(ctx.to_device(key))
+    d_ct = ctx.to_device(ct)
+    whole = H(ctx.keyswitch(key_dual, d_ct, w))
+    rows = []
+    for rank in range(world):
+        lo, hi = S.shard_range(ctx.L, rank, world)
+        shard = T.Context(N, qs[lo:hi], psis[lo:hi])
+        rows.append(H(ctx.keyswitch_shard(shard, lo, S.key_rows_for_shard(key_dual, lo, hi), d_ct, w)))
+    assert np.array_equal(np.concatenate(rows, axis=-2), whole)
+    if N <= 1024:
+        for b in range(B):
+            dg = orc.keyswitch_digits(ct[b, comps - 1], w)
+            c2 = ct[b, 1] if comps == 3 else np.zeros_like(ct[b, 0])
+            w1, w2 = orc.keyswitch_accum(dg, key, ct[b, 0], c2)
+            assert np.array_equal(whole[b, 0], w1) and np.array_equal(whole[b, 1], w2)
+    with pytest.raises(T.EngineError):
+        ctx.keyswitch_shard(T.Context(N, qs[:1], psis[:1]), 1, S.key_rows_for_shard(key_dual, 0, 1), d_ct, w)   # wrong offset
+
+
 def test_keyswitch_modulus_raised_matches_python_oracle():
     # test/ckks_modraise.jl shape: N = 32, (q0, q1, special), CRT digits
     N = 32

@@ -86,3 +86,51 @@ def test_shard_range_properties():
             assert [S.shard_range(n, r, w)[0] for r in range(w)] == [sum(sizes[:r]) for r in range(w)]
     with pytest.raises(ValueError):
         S.shard_range(4, 2, 2)
+
+
+def _ks_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import toyfhe_b200 as T
+        from toyfhe_b200 import sharding as S
+        from oracle import c_oracle as CO
+        N, w = 16, 7
+        qs, psis = T.prime_chain(N, [50, 50, 50])
+        L = len(qs)
+        orc = CO.Rns(N, qs, psis)
+        rng = np.random.default_rng(3)     # same seed on every rank: the ciphertext and the key are replicated here
+
+        def rnd(shape):
+            out = np.empty(shape + (L, N), dtype=np.uint64)
+            for i, q in enumerate(qs):
+                out[..., i, :] = rng.integers(0, q, size=shape + (N,), dtype=np.uint64)
+            return out
+
+        ct = rnd((1, 3))
+        D = CO.ndigits(qs, w)
+        key = rnd((D, 2))
+        # the reference algorithm on the whole ring (rlwe_she.jl:315-347): [1][2][L][N]
+        w1, w2 = orc.keyswitch_accum(orc.keyswitch_digits(ct[0, 2], w), key, ct[0, 0], ct[0, 1])
+        want = np.stack([w1, w2])[None]
+
+        def shard_op(lo, hi):                                 # rows lo..hi-1 (the oracle stands in for tfb_keyswitch_shard)
+            return torch.from_numpy(np.ascontiguousarray(want[:, :, lo:hi, :]).view(np.int64))
+
+        res = S.keyswitch_residue_sharded(shard_op, L)
+        assert res.shape == (1, 2, L, N)
+        assert np.array_equal(res.numpy().view(np.uint64), want)
+        krows = S.key_rows_for_shard(torch.from_numpy(key.view(np.int64)), *S.shard_range(L, rank, world))
+        assert krows.shape == (D, 2, S.shard_sizes(L, world)[rank], N) and krows.is_contiguous()
+        np.save(os.path.join(outdir, f"ok{rank}.npy"), np.array([1]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_residue_sharded_keyswitch_gather_over_gloo(tmp_path, world):
+    """prime rows computed per rank (ragged: 3 primes over 2 ranks) are assembled by one all-gather"""
+    mp.spawn(_ks_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}.npy") for r in range(world))

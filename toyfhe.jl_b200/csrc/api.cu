@@ -605,6 +605,41 @@ int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual
     return launch_ks_finish(c, ct, comps, acc, out, batch, st);
 }
 
+int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
+                        uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c); CHECK_CTX(r);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(key_dual); CHECK_PTR(ct); CHECK_PTR(out);
+    if (comps != 2 && comps != 3) { tfb_set_error("keyswitch: ciphertext must have 2 or 3 components"); return TFB_EINVAL; }
+    if (r->N != c->N || r->L == 0 || (u64)first + r->L > c->L) { tfb_set_error("keyswitch_shard: shard primes out of range"); return TFB_EINVAL; }
+    for (u32 i = 0; i < r->L; i++)
+        if (r->q[i] != c->q[first + i]) { tfb_set_error("keyswitch_shard: shard ring must hold the primes first.. of the ciphertext ring"); return TFB_EINVAL; }
+    uint32_t Dneed = c->L;
+    if (w) {
+        int rc = tfb_ndigits(c->q.data(), c->L, w, &Dneed);
+        if (rc) return rc;
+    }
+    if (D < Dneed) { tfb_set_error("keyswitch: evaluation key has too few digit components"); return TFB_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t polyr = (size_t)r->L * r->N, polyc = (size_t)c->L * c->N;
+    u32 dch = (u32)((size_t)(1ull << 30) / (batch * polyr * sizeof(u64)));
+    if (dch < 1) dch = 1;
+    if (dch > Dneed) dch = Dneed;
+    int rc = stage_reserve(r, (2 * batch * polyr + (size_t)dch * batch * polyr) * sizeof(u64));
+    if (rc) return rc;
+    u64* acc = (u64*)r->stage;
+    u64* dig = acc + 2 * batch * polyr;
+    const u64* cend = ct + (size_t)(comps - 1) * polyc;
+    for (u32 k0 = 0; k0 < Dneed; k0 += dch) {
+        const u32 dn = Dneed - k0 < dch ? Dneed - k0 : dch;
+        if ((rc = launch_ks_digits(c, r, (int)w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;   // digits of the WHOLE integer, embedded in the shard's primes
+        if ((rc = launch_ntt(r, dig, dig, (u64)batch * dn * r->L, false, st))) return rc;
+        if ((rc = launch_ks_accum(r, k0, dn, dig, key_dual, acc, k0 ? 1 : 0, batch, st))) return rc;
+    }
+    if ((rc = launch_ntt(r, acc, acc, 2 * batch * r->L, true, st))) return rc;
+    return launch_ks_finish(r, ct, comps, acc, out, batch, st, c->L, first);
+}
+
 // ---------------------------------------------------------- host-buffer variants
 #define H2D(dst, src, words) TFB_CUDA(cudaMemcpyAsync(dst, src, (words) * sizeof(u64), cudaMemcpyHostToDevice, st))
 #define D2H(dst, src, words) TFB_CUDA(cudaMemcpyAsync(dst, src, (words) * sizeof(u64), cudaMemcpyDeviceToHost, st))

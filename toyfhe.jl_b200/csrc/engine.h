@@ -85,7 +85,7 @@ int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct
                      u64 batch, cudaStream_t st);
 int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
                     cudaStream_t st);
-int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st);
+int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st, u32 Lct = 0, u32 first = 0);
 int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch,
                             cudaStream_t st);
 int build_garner(tfb_ctx* c);

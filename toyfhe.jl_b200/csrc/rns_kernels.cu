@@ -669,9 +669,10 @@ int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, 
 // plain params:      out[b][k] = (k < comps-1 ? ct[b][k] : 0) + acc[b][k]            (rlwe_she.jl:323-324,343-346)
 // ModulusRaised:     v = P * ct[b][k] (+0 on the special row) + acc_ext[b][k];  out = modswitch(v)
 //                    (modulusraising.jl:35-42 with crt.jl:215-220)
+// (shards: acc/out cover the primes first..first+L-1 of a ciphertext with Lct primes, pp = the shard's primes)
 __global__ void ks_finish_kernel(const u64* __restrict__ ct, const u32 comps, const u64* __restrict__ acc,
                                  u64* __restrict__ out, const u32 L, const u32 logN,
-                                 const PrimeParams* __restrict__ pp, const u64 total) {
+                                 const PrimeParams* __restrict__ pp, const u64 total, const u32 Lct, const u32 first) {
     const u32 N = 1u << logN;
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
@@ -682,7 +683,7 @@ __global__ void ks_finish_kernel(const u64* __restrict__ ct, const u32 comps, co
         const u64 b = bk >> 1;
         const u64 q = pp[i].pc.q;
         u64 v = acc[idx];
-        if (k + 1 < comps) v = add_mod(v, ct[(((b * comps + k) * L + i) << logN) + n], q);
+        if (k + 1 < comps) v = add_mod(v, ct[(((b * comps + k) * Lct + first + i) << logN) + n], q);
         out[idx] = v;
     }
 }
@@ -710,11 +711,11 @@ __global__ void ks_finish_raised_kernel(const u64* __restrict__ ct, const u32 co
     }
 }
 
-int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st) {
+int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st, u32 Lct, u32 first) {
     if (!batch) return TFB_OK;
     const u64 total = batch * 2 * c->L * c->N;
     const unsigned tb = 256, nb = grid_for(total, tb);
-    { ProfScope ps(PC_KS_FINISH, st); ks_finish_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, out, c->L, c->logN, c->d_pp, total); }
+    { ProfScope ps(PC_KS_FINISH, st); ks_finish_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, out, c->L, c->logN, c->d_pp, total, Lct ? Lct : c->L, first); }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
-    "tfb_keyswitch_digits", "tfb_keyswitch",
+    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard",
     "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
     "tfb_bfv_mul_host", "tfb_rescale_host",
 ]
@@ -293,6 +293,16 @@ class Context:
         out = self.empty(tuple(ct.shape[:-3]) + (2, self.L, self.N)) if out is None else out
         _check(self._lib.tfb_keyswitch(self.h, ext.h if ext is not None else None, C.c_uint32(w), _ptr(key_dual),
                                        C.c_uint32(D), _ptr(ct), C.c_uint32(comps), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    def keyswitch_shard(self, shard: "Context", first: int, key_dual_shard, ct, w: int, out=None, stream=None):
+        """Rows first..first+shard.L-1 of keyswitch(key, ct): ct [B][comps][L][N] whole, key_dual_shard [D][2][Ls][N]."""
+        comps = ct.shape[-3]
+        B = self._batch(ct, comps)
+        out = shard.empty(tuple(ct.shape[:-3]) + (2, shard.L, self.N)) if out is None else out
+        _check(self._lib.tfb_keyswitch_shard(self.h, shard.h, C.c_uint32(first), C.c_uint32(w), _ptr(key_dual_shard),
+                                             C.c_uint32(key_dual_shard.shape[0]), _ptr(ct), C.c_uint32(comps), _ptr(out),
+                                             C.c_uint64(B), _stream_ptr(stream)))
         return out
 
     # -- host-buffer entry points (numpy uint64 or pinned torch tensors)

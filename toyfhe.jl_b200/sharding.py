@@ -109,3 +109,41 @@ def sharded_apply(op: Callable[..., torch.Tensor], batch: int, inputs: Sequence[
         if res is None:
             res = torch.empty((0, *[int(v) for v in meta.tolist()]), dtype=shards[0].dtype, device=shards[0].device)
     return gather_batch(res, batch, dst=root, group=group)
+
+
+# --------------------------------------------------------------------------- residue-parallel keyswitch
+# BASELINE config 4 ("residues sharded 2/4/8 GPU"): ONE ciphertext (or a small batch) is
+# key-switched by all ranks together.  Rank r owns the contiguous primes shard_range(L, r, world); the ciphertext is
+# replicated (2-3 MiB), the evaluation key -- the large object, D*2*L*N words -- is split by prime rows so each rank
+# holds and streams only its part.  Every rank extracts the digits of the whole integer itself (rlwe_she.jl:328-337
+# needs all residues of a coefficient; recomputing them is cheaper than exchanging them), transforms and accumulates
+# them under its own primes, and the result rows are assembled with ONE all-gather -- the only data-path collective.
+
+def key_rows_for_shard(key_dual: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """key_dual [D][2][L][N] -> the contiguous copy [D][2][hi-lo][N] a rank keeps"""
+    return key_dual[:, :, lo:hi, :].contiguous()
+
+
+def allgather_prime_rows(local: torch.Tensor, L: int, group=None) -> torch.Tensor:
+    """local [..., Ls, N] (this rank's prime rows, ragged over ranks) -> [..., L, N] on every rank."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = shard_sizes(L, world)
+    mx = max(sizes)
+    lead, N = tuple(local.shape[:-2]), local.shape[-1]
+    pad = torch.zeros(lead + (mx, N), dtype=local.dtype, device=local.device)
+    pad[..., : local.shape[-2], :] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[..., :s, :] for p, s in zip(parts, sizes) if s > 0], dim=-2).contiguous()
+
+
+def keyswitch_residue_sharded(shard_op: Callable[[int, int], torch.Tensor], L: int, group=None) -> torch.Tensor:
+    """`shard_op(lo, hi)` computes rows lo..hi-1 of the key-switched ciphertext ([B][2][hi-lo][N]); on a GPU it is
+    `lambda lo, hi: ctx.keyswitch_shard(shard_ctx, lo, key_rows, ct, w)`.  Returns [B][2][L][N] on every rank."""
+    rank, world = _world(group)
+    lo, hi = shard_range(L, rank, world)
+    if hi <= lo:
+        raise ValueError("more ranks than RNS primes: residue sharding needs world <= L")
+    return allgather_prime_rows(shard_op(lo, hi), L, group=group)
