@@ -143,6 +143,14 @@ int tfb_bfv_contract(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_
  * (rlwe_she.jl:247-262 with bfv.jl:34-40): c1,c2 [batch][2][L][N] -> out [batch][3][L][N] */
 int tfb_bfv_mul(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
 
+/* BFV plaintext maps.  Delta is the BFVParams field of the reference (bfv.jl:5-15;
+ * floor(Q/t) in test/bfv_crt.jl:25-32 and bfv.jl:118), passed as n_limbs little-endian 64-bit words; Q/Delta < 2^40.
+ * pi^-1 (bfv.jl:21-24): m [polys][N] (any words; reduced mod t) -> Delta * m over ctx's primes, out [polys][L][N].
+ * pi (bfv.jl:26-29): b [polys][L][N] primal -> mod(divround(SignedMod(b_n), Delta), t), out [polys][N], with the
+ * centred lift of signedmod.jl:12-19 and round-half-away-from-zero of div_hacks.jl:120-135; exact. */
+int tfb_bfv_encode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream);
+int tfb_bfv_decode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
+
 /* ---- key switching ------------------------------------------------------------ */
 /* Digit polynomials of keyswitch (rlwe_she.jl:326-338).  cend = last ciphertext
  * component [batch][L][N] (primal, contiguous); relin_window w == 0 -> CRT digits

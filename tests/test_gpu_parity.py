@@ -218,6 +218,43 @@ def test_bfv_mul_joint_basis_equals_callers_basis(N, L, Lb, t):
     assert np.array_equal(slow, want)
 
 
+# --------------------------------------------------------------------- BFV plaintext maps (bfv.jl:21-29)
+def _to_rns(xs, qs):
+    return np.array([[x % q for x in xs] for q in qs], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("N,logqs,t", [(64, [60, 60, 40], 53), (1024, [60] * 8, 65537), (32, [50, 50], 256), (16, [40], 7),
+                                       (64, [60, 60], (1 << 31) - 1)])
+def test_bfv_encode_decode(N, logqs, t):
+    """pi^-1 = Delta*m and pi = mod(divround(SignedMod(x), Delta), t): bit-exact against big-integer arithmetic on
+    random values, exact ties (2r == Delta), neighbours of ties, 0, +-1 and the ends of the centred range"""
+    import math
+    qs, psis, ctx, orc = _ring(N, logqs)
+    Q = math.prod(qs)
+    rng = np.random.default_rng(N + t)
+    for delta in (Q // t, Q // t + 1, (Q // t) | 1, (Q // t) & ~1):     # floor(Q/t) as in the reference's tests, odd and even
+        m = rng.integers(0, 1 << 63, size=(3, N), dtype=np.uint64)
+        got = H(ctx.bfv_encode(t, delta, ctx.to_device(m)))
+        for p in range(3):
+            assert np.array_equal(got[p], _to_rns([delta * (int(v) % t) for v in m[p]], qs))
+        xs = [int.from_bytes(rng.bytes(80), "little") % Q for _ in range(N)]
+        half = delta // 2
+        special = [0, 1, Q - 1, Q // 2, Q // 2 + 1, Q // 2 - 1, delta, delta - 1, delta + 1, half, half + 1, half - 1 if half else 0,
+                   Q - half, Q - half - 1, Q - half + 1, 5 * delta + half, 5 * delta + half + 1, 5 * delta + half - 1,
+                   Q - (7 * delta + half), Q - (7 * delta + half) - 1, Q - (7 * delta + half) + 1, (t // 2) * delta, (t // 2) * delta + half]
+        for i, v in enumerate(special[:N]):
+            xs[i] = v % Q
+        want = [O.rha(O.centre(x, Q), delta) % t for x in xs]
+        got = H(ctx.bfv_decode(t, delta, ctx.to_device(_to_rns(xs, qs)[None])))[0]
+        assert [int(v) for v in got] == want
+        # round trip through the plaintext maps alone (no noise): decode(encode(m)) = m mod t
+        back = H(ctx.bfv_decode(t, delta, ctx.bfv_encode(t, delta, ctx.to_device(m))))
+        if delta == Q // t:
+            assert np.array_equal(back, m % np.uint64(t))
+    with pytest.raises(T.EngineError):
+        ctx.bfv_decode(t, 1, ctx.to_device(_to_rns([0] * N, qs)[None]))          # Delta far too small for a word-size quotient
+
+
 # --------------------------------------------------------------------- key switching
 @pytest.mark.parametrize("w", [0, 1, 2, 7, 31])
 def test_keyswitch_digits(w):

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import toyfhe_b200 as T
+from oracle import c_oracle as CO
 from oracle import toyfhe_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -45,6 +46,45 @@ def test_bfv_crt_replay():
     hooks = params.mul_contract(acc)
     for a, b in zip(hooks, y.cs):
         assert np.array_equal(a.residues(), b.residues())
+
+
+def test_bfv_simd_replay():
+    """test/bfv_simd.jl:10-31 (BASELINE config "BFV SIMD") over the word-size RNS route: SlotEncoding plaintexts
+    (slots = values at psi_t^(2k+1), t = 65537), encrypt, ciphertext multiply, decrypt, read the slots back.
+    Encoding (NTT over F_t), pi^-1, the multiply and pi all run on the device."""
+    n, t = 4096, 65537
+    chain = [O.nextprime((1 << 60) + 1, 2 * n)]
+    while len(chain) < 7:
+        chain.append(O.nextprime(chain[-1] + 2 * n, 2 * n))
+    R = T.NegacyclicRing(n, qs=chain[:2])          # Q ~ 2^120
+    Rbig = T.NegacyclicRing(n, qs=chain[2:])       # 5 primes: P_big ~ 2^300 > N Q^2
+    Rplain = T.NegacyclicRing(n, qs=[t])           # psi = minimal primitive 2N-th root mod t (pow2_cyc_rings.jl:38-41)
+    params = T.BFVParams(R, Rbig, t, relin_window=1, sigma=3.2)
+    s = T.Sampler(7)
+    kp = T.keygen(s, params)
+    plain = T.SlotEncoding(Rplain)
+    plain[0] = 1
+    plain[1] = 1
+    plain2 = T.SlotEncoding(Rplain)
+    plain2[:] = 10
+    plain2[0] = 5
+    c1, c2 = T.encrypt(s, kp, plain), T.encrypt(s, kp, plain2)
+    y = c1 * c2
+    data = T.SlotEncoding.from_coeffs(Rplain, T.decrypt(kp, y))
+    assert data[0] == 5 and data[1] == 10
+    assert all(v == 0 for v in data.slots[2:])
+    # the slot maps invert each other and follow the oracle's NTT definition over F_t
+    orc = CO.Rns(n, [t], Rplain.psis)
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, t, size=n, dtype=np.uint64)
+    se = T.SlotEncoding(Rplain, v)
+    assert se.coeffs() == [int(x) for x in orc.inntt(v.reshape(1, 1, n)).reshape(-1)]
+    assert T.SlotEncoding.from_coeffs(Rplain, se.coeffs()).slots == [int(x) for x in v]
+    # full-width SIMD: slot-wise product of two random slot vectors
+    a, b = rng.integers(0, t, size=n, dtype=np.uint64), rng.integers(0, t, size=n, dtype=np.uint64)
+    prod = T.encrypt(s, kp, T.SlotEncoding(Rplain, a)) * T.encrypt(s, kp, T.SlotEncoding(Rplain, b))
+    got = T.SlotEncoding.from_coeffs(Rplain, T.decrypt(kp, prod)).slots
+    assert got == [int(x) * int(y) % t for x, y in zip(a, b)]
 
 
 def test_bfv_keyswitch_replay():

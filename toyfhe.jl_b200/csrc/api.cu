@@ -455,6 +455,19 @@ int tfb_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* in, u
     return launch_bfv_contract(cq, cb, t, in, out, polys, (cudaStream_t)stream);
 }
 
+int tfb_bfv_encode(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(delta); CHECK_PTR(m); CHECK_PTR(out);
+    return launch_bfv_encode(c, t, delta, nl, m, out, polys, (cudaStream_t)stream);
+}
+int tfb_bfv_decode(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(delta); CHECK_PTR(b); CHECK_PTR(out);
+    return launch_bfv_decode(c, t, delta, nl, b, out, polys, (cudaStream_t)stream);
+}
+
 // batch chunk so that the R_big intermediates (7 polys per pair) stay bounded
 static u64 bfv_chunk(const tfb_ctx* cb, u64 batch) {
     const size_t per = 7 * (size_t)cb->L * cb->N * sizeof(u64);

@@ -735,3 +735,135 @@ int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, 
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
+
+// ---------------------------------------- BFV plaintext maps (bfv.jl:21-29)
+// pi^-1:  m in Z_t^N  ->  Delta * m  embedded in every prime          (bfv.jl:21-24)
+// pi:     b in R_Q    ->  mod(divround(SignedMod(b_n), Delta), t)     (bfv.jl:26-29; rounding div_hacks.jl:120-135,
+//                                                                       centred lift signedmod.jl:12-19)
+// Exact decode in word arithmetic.  |x| = X or Q - X (X > floor(Q/2));  a = |x| + floor(Delta/2) < Q;
+// y = floor(a / Delta) = round-half-away(|x| / Delta) for either parity of Delta.  y is small (about t/2), so it is
+// estimated from the two leading mixed-radix digits of a and then CORRECTED with exact sign tests of
+// rho(y) = a - y Delta (one Garner conversion each; |rho| << Q/2 near the true y, so "canonical value above Q/2"
+// means negative): the loops below stop at the largest y with rho(y) >= 0 whatever the error of the estimate.
+struct PlainArgs {
+    u64 dm[MAXD];    // Delta mod q_i
+    u64 hd[MAXD];    // floor(Delta/2) mod q_i
+    double ratio1;   // (prod_{k<L-1} q_k) / Delta
+    double ratio2;   // (prod_{k<L-2} q_k) / Delta   (0 if L == 1)
+};
+__global__ void bfv_encode_kernel(const u64* __restrict__ m, u64* __restrict__ out, const u32 L, const u32 logN, const u64 t,
+                                  const PrimeParams* __restrict__ pp, const PlainArgs pa, const u64 total) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (p, i)
+        const u32 i = (u32)(r % L);
+        const u64 p = r / L;
+        const PrimeConst pc = pp[i].pc;
+        out[idx] = barrett_mul((m[(p << logN) + n] % t) % pc.q, pa.dm[i], pc);
+    }
+}
+__device__ __forceinline__ bool plain_rho_nonneg(const u64* a, const u64 y, u64* tmp, u64* dg, const u32 L, const GarnerTab g,
+                                                 const PrimeParams* __restrict__ pp, const PlainArgs& pa) {
+    for (u32 i = 0; i < L; i++) {
+        const PrimeConst pc = pp[i].pc;
+        tmp[i] = sub_mod(a[i], barrett_mul(y % pc.q, pa.dm[i], pc), pc.q);
+    }
+    garner_digits(tmp, dg, L, g, pp);
+    return !mr_above_half(dg, L, g.halfmr);
+}
+__global__ void bfv_decode_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 L, const u32 logN, const u64 t,
+                                  const GarnerTab g, const PrimeParams* __restrict__ pp, const PlainArgs pa, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 a[MAXD], tmp[MAXD], dg[MAXD];
+    for (u32 i = 0; i < L; i++) a[i] = in[((p * L + i) << logN) + n];
+    garner_digits(a, dg, L, g, pp);
+    const bool neg = mr_above_half(dg, L, g.halfmr);
+    for (u32 i = 0; i < L; i++) {
+        const u64 q = pp[i].pc.q;
+        a[i] = add_mod(neg ? neg_mod(a[i], q) : a[i], pa.hd[i], q);
+    }
+    garner_digits(a, dg, L, g, pp);
+    double est = (double)dg[L - 1] * pa.ratio1;
+    if (L > 1) est += (double)dg[L - 2] * pa.ratio2;
+    u64 y = est > 0.0 ? (u64)est : 0;
+    while (y > 0 && !plain_rho_nonneg(a, y, tmp, dg, L, g, pp, pa)) y--;
+    while (plain_rho_nonneg(a, y + 1, tmp, dg, L, g, pp, pa)) y++;
+    const u64 ym = y % t;
+    out[idx] = (neg && ym) ? t - ym : ym;
+}
+
+// host: little-endian multi-word helpers for Delta (a free BFVParams field in the reference, bfv.jl:5-15)
+static u64 limbs_mod(const u64* x, u32 n, u64 m) {
+    u128 r = 0;
+    for (int i = (int)n - 1; i >= 0; i--) r = ((r << 64) | x[i]) % m;
+    return (u64)r;
+}
+static long double limbs_ld(const std::vector<u64>& x) {
+    long double v = 0;
+    for (int i = (int)x.size() - 1; i >= 0; i--) v = v * 18446744073709551616.0L + (long double)x[i];
+    return v;
+}
+static void limbs_mul(std::vector<u64>& x, u64 m) {
+    u64 carry = 0;
+    for (auto& w : x) {
+        const u128 cur = (u128)w * m + carry;
+        w = (u64)cur;
+        carry = (u64)(cur >> 64);
+    }
+    if (carry) x.push_back(carry);
+}
+static int plain_args(tfb_ctx* c, const u64* delta, u32 nl, PlainArgs* pa) {
+    if (c->L > MAXD || !c->conv_ok) { tfb_set_error("bfv plaintext maps: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    while (nl > 0 && delta[nl - 1] == 0) nl--;
+    if (nl == 0) { tfb_set_error("bfv plaintext maps: Delta must be positive"); return TFB_EINVAL; }
+    std::vector<u64> d(delta, delta + nl), half(nl);
+    u64 carry = 0;
+    for (int i = (int)nl - 1; i >= 0; i--) {
+        half[i] = (d[i] >> 1) | (carry << 63);
+        carry = d[i] & 1;
+    }
+    std::vector<u64> W1{1}, W2{1};
+    for (u32 k = 0; k + 1 < c->L; k++) limbs_mul(W1, c->q[k]);
+    for (u32 k = 0; k + 2 < c->L; k++) limbs_mul(W2, c->q[k]);
+    std::vector<u64> Q = W1;
+    limbs_mul(Q, c->q[c->L - 1]);
+    const long double dl = limbs_ld(d);
+    if (dl * 1099511627776.0L < limbs_ld(Q)) { tfb_set_error("bfv plaintext maps: Delta too small (Q / Delta must stay below 2^40)"); return TFB_EUNSUPPORTED; }
+    for (u32 i = 0; i < c->L; i++) {
+        pa->dm[i] = limbs_mod(d.data(), nl, c->q[i]);
+        pa->hd[i] = limbs_mod(half.data(), nl, c->q[i]);
+    }
+    pa->ratio1 = (double)(limbs_ld(W1) / dl);
+    pa->ratio2 = c->L > 1 ? (double)(limbs_ld(W2) / dl) : 0.0;
+    return TFB_OK;
+}
+int launch_bfv_encode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* m, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (t == 0) { tfb_set_error("bfv encode: plaintext modulus must be positive"); return TFB_EINVAL; }
+    PlainArgs pa;
+    int rc = plain_args(c, delta, nl, &pa);
+    if (rc) return rc;
+    const u64 total = polys * c->L * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    { ProfScope ps(PC_ELEMENTWISE, st); bfv_encode_kernel<<<nb, tb, 0, st>>>(m, out, c->L, c->logN, t, c->d_pp, pa, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+int launch_bfv_decode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (t == 0) { tfb_set_error("bfv decode: plaintext modulus must be positive"); return TFB_EINVAL; }
+    PlainArgs pa;
+    int rc = plain_args(c, delta, nl, &pa);
+    if (rc) return rc;
+    const u64 total = polys * c->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_BFV_CONTRACT, st); bfv_decode_kernel<<<(unsigned)nb, tb, 0, st>>>(in, out, c->L, c->logN, t, garner_of(c), c->d_pp, pa, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}

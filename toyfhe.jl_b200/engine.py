@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
-    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard",
+    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_bfv_encode", "tfb_bfv_decode",
     "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
     "tfb_bfv_mul_host", "tfb_rescale_host",
 ]
@@ -274,6 +274,31 @@ class Context:
         B = self._batch(c1, 2)
         out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
         _check(self._lib.tfb_bfv_mul(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    # -- BFV plaintext maps (bfv.jl:21-29)
+    @staticmethod
+    def _limbs(x: int):
+        x = int(x)
+        if x <= 0:
+            raise EngineError("Delta must be a positive integer")
+        n = (x.bit_length() + 63) // 64
+        arr = (C.c_uint64 * n)(*[(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)])
+        return arr, n
+
+    def bfv_encode(self, t: int, delta: int, m, out=None, stream=None):
+        """m [polys][N] (words, reduced mod t) -> Delta*m over this ring's primes [polys][L][N]"""
+        arr, n = self._limbs(delta)
+        polys = int(m.numel() // self.N)
+        out = self.empty(tuple(m.shape[:-1]) + (self.L, self.N)) if out is None else out
+        _check(self._lib.tfb_bfv_encode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream)))
+        return out
+
+    def bfv_decode(self, t: int, delta: int, b, out=None, stream=None):
+        """b [polys][L][N] primal -> mod(divround(SignedMod(b), Delta), t) [polys][N]"""
+        arr, n = self._limbs(delta)
+        out = self.empty(tuple(b.shape[:-2]) + (self.N,)) if out is None else out
+        _check(self._lib.tfb_bfv_decode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
         return out
 
     # -- key switching

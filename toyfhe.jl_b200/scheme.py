@@ -99,12 +99,24 @@ class BFVParams(SHEShemeParams):
     def R_cipher(self): return self.R
     def R_plain(self): return self.t
 
+    def _on_device(self) -> bool:
+        # engine limits of tfb_bfv_encode / tfb_bfv_decode: word-size t, Q / Delta < 2^40
+        return 0 < self.t < (1 << 63) and (self.Delta << 40) >= self.R.modulus()
+
     def pi_inv(self, plaintext: Sequence[int]) -> RingElement:
-        """Delta * plaintext (bfv.jl:21-24)"""
-        return self.R([self.Delta * (int(m) % self.t) for m in plaintext])
+        """Delta * plaintext (bfv.jl:21-24) -- on the device (tfb_bfv_encode)"""
+        if not self._on_device():
+            return self.R([self.Delta * (int(m) % self.t) for m in plaintext])
+        ctx = self.R.ctx
+        m = ctx.to_device(np.array([int(v) % self.t for v in plaintext], dtype=np.uint64).reshape(1, self.R.N))
+        return RingElement(self.R, primal=ctx.bfv_encode(self.t, self.Delta, m)[0])
 
     def pi(self, b: RingElement) -> List[int]:
-        """mod(divround(SignedMod(x), Delta), t) (bfv.jl:26-29; rounding div_hacks.jl:120-135)"""
+        """mod(divround(SignedMod(x), Delta), t) (bfv.jl:26-29; rounding div_hacks.jl:120-135) -- on the device
+        (tfb_bfv_decode); the big-integer loop below is only the route for parameters outside the engine's limits"""
+        if self._on_device():
+            ctx = self.R.ctx
+            return [int(v) for v in ctx.to_host(ctx.bfv_decode(self.t, self.Delta, b.coeffs_primal()))]
         out = []
         for x in b.to_signed_ints():
             qq, r = divmod(abs(x), self.Delta)
@@ -254,6 +266,43 @@ class CipherText:
 # ----------------------------------------------------------------------------
 # key generation, encryption, decryption (rlwe_she.jl:151-216)
 # ----------------------------------------------------------------------------
+class SlotEncoding:
+    """encoding.jl:28-56: a BFV plaintext given by its SLOTS, the values of the plaintext polynomial at
+    psi_t^(2k+1), k = 0..N-1 -- the dual (NTT-domain) coefficients of the plaintext ring element over F_t
+    (t prime, 2N | t-1, encoding.jl:35-43).  Slot-wise products of plaintexts are ring products, so a ciphertext
+    multiply acts on all N slots at once (test/bfv_simd.jl).  Both directions run on the device (one inverse /
+    forward NTT over the plaintext ring's own context)."""
+
+    def __init__(self, plain_ring: NegacyclicRing, slots: Optional[Sequence[int]] = None):
+        if plain_ring.L != 1:
+            raise UsageError("SlotEncoding needs a single-prime plaintext ring (encoding.jl:38-41)")
+        self.ring = plain_ring
+        self.t = plain_ring.qs[0]
+        self.slots = [0] * plain_ring.N if slots is None else [int(v) % self.t for v in slots]
+        assert len(self.slots) == plain_ring.N
+
+    def __getitem__(self, i): return self.slots[i]
+    def __setitem__(self, i, v):
+        if isinstance(i, slice):
+            idx = range(*i.indices(len(self.slots)))
+            vals = [v] * len(idx) if isinstance(v, (int, np.integer)) else list(v)
+            for k, x in zip(idx, vals):
+                self.slots[k] = int(x) % self.t
+        else:
+            self.slots[i] = int(v) % self.t
+    def __len__(self): return len(self.slots)
+
+    def coeffs(self) -> List[int]:
+        """convert(RingElement, s): primal coefficients of the element whose dual is the slot vector (encoding.jl:49-56)"""
+        return self.ring.from_residues(np.array([self.slots], dtype=np.uint64), dual=True).to_ints()
+
+    @classmethod
+    def from_coeffs(cls, plain_ring: NegacyclicRing, coeffs: Sequence[int]) -> "SlotEncoding":
+        """SlotEncoding(r): the dual coefficients of plaintext r (encoding.jl:35-43)"""
+        el = plain_ring([int(c) for c in coeffs])
+        return cls(plain_ring, [int(v) for v in E.Context.to_host(el.coeffs_dual()).reshape(-1)])
+
+
 def keygen(s: Sampler, params: SHEShemeParams) -> KeyPair:
     """rlwe_she.jl:155-167"""
     R = params.R_key()
@@ -285,6 +334,8 @@ def encrypt(s: Sampler, key, plaintext) -> CipherText:
     if isinstance(plaintext, CKKSEncoding):
         tag = CKKSScale(plaintext.scale)
         plaintext = plaintext.to_ring_element(pk.params.R_cipher())
+    if isinstance(plaintext, SlotEncoding):
+        plaintext = plaintext.coeffs()
     m = pk.params.pi_inv(plaintext)
     return CipherText(pk.params, (c.cs[0] + m,) + c.cs[1:], tag)
 
