@@ -56,7 +56,8 @@ int tfb_profile_classes(void);
 const char* tfb_profile_class_name(int cls);
 int tfb_profile_read(unsigned long long* counts, double* total_ms, int reset);
 /* testing hook: route base conversions through the generic runtime-L kernels even
- * where a register-resident specialisation exists (both must agree bit for bit) */
+ * where a register-resident specialisation exists (on = 1), or keep the specialised kernels but reduce 128-bit sums with
+ * the generic Shoup/Barrett step instead of the Solinas folds used on 2^60 + e primes (on = 2); all must agree bit for bit */
 int tfb_debug_force_generic(int on);
 /* kernel selection hook for N >= 2^14: 1 = one CTA per row (512 threads x 32 residues), 2 = persistent TMA-prefetched
  * 1024x16 kernels, 3 (default) = persistent TMA-prefetched 512x32 kernels */

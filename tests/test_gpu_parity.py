@@ -209,13 +209,42 @@ def test_bfv_mul_joint_basis_equals_callers_basis(N, L, Lb, t):
     want = CO.bfv_mul(oq, ob, t, c1, c2)
     d1, d2 = cq.to_device(c1), cq.to_device(c2)
     fast = H(cq.bfv_mul(cb, t, d1, d2))
-    T.force_generic(True)
+    T.force_generic(1)
     try:
         slow = H(cq.bfv_mul(cb, t, d1, d2))
+        T.force_generic(2)                            # joint-basis kernels without the Solinas folds
+        mid = H(cq.bfv_mul(cb, t, d1, d2))
     finally:
-        T.force_generic(False)
+        T.force_generic(0)
     assert np.array_equal(fast, want)
     assert np.array_equal(slow, want)
+    assert np.array_equal(mid, want)
+
+
+def test_bfv_mul_joint_basis_extreme_residues():
+    """the 128-bit sums of the joint-basis kernels are reduced by Solinas folds at bit 60: all-(q-1) operands and
+    operands whose tensor values sit at +-Q/2 maximise every accumulation; headline shape (L = 8, K = 9)"""
+    N, L, Lb, t = 256, 8, 17, 65537
+    allq, allpsi = T.prime_chain(N, [60] * (L + Lb))
+    qs, psis, qb, psib = allq[:L], allpsi[:L], allq[L:], allpsi[L:]
+    cq, cb = T.Context(N, qs, psis), T.Context(N, qb, psib)
+    oq, ob = CO.Rns(N, qs, psis), CO.Rns(N, qb, psib)
+    c1 = np.empty((4, 2, L, N), dtype=np.uint64)
+    c2 = np.empty_like(c1)
+    Q = math.prod(qs)
+    rng = np.random.default_rng(3)
+    for i, q in enumerate(qs):
+        c1[0, :, i, :] = q - 1
+        c2[0, :, i, :] = q - 1
+        c1[1, :, i, :] = (Q >> 1) % q
+        c2[1, :, i, :] = ((Q >> 1) + 1) % q
+        c1[2, :, i, :] = rng.integers(0, q, size=(2, N), dtype=np.uint64)
+        c2[2, :, i, :] = q - 1
+        c1[3, :, i, :] = 0
+        c2[3, :, i, :] = rng.integers(0, q, size=(2, N), dtype=np.uint64)
+    want = CO.bfv_mul(oq, ob, t, c1, c2)
+    got = H(cq.bfv_mul(cb, t, cq.to_device(c1), cq.to_device(c2)))
+    assert np.array_equal(got, want)
 
 
 # --------------------------------------------------------------------- BFV plaintext maps (bfv.jl:21-29)

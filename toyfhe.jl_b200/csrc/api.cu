@@ -134,8 +134,9 @@ int tfb_debug_ntt_force_harvey(int on) {
     return TFB_OK;
 }
 int tfb_debug_force_generic(int on) {
-    extern bool g_force_generic;
-    g_force_generic = on != 0;
+    extern bool g_force_generic, g_force_generic_red;
+    g_force_generic = on == 1;        // 1: generic runtime-L conversion kernels
+    g_force_generic_red = on == 2;    // 2: specialised kernels, but Shoup/Barrett reductions even on 2^60 + e primes
     return TFB_OK;
 }
 const char* tfb_profile_class_name(int i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }

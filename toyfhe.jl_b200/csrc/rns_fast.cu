@@ -18,6 +18,8 @@
 
 #include "engine.h"
 
+bool g_force_generic_red = false;  // testing hook: Shoup/Barrett reductions even on 2^60 + e primes
+
 __device__ __forceinline__ u64 red128(u128 a, const PrimeConst& pc) {
     return red128_any((u64)(a >> 64), (u64)a, pc);
 }
@@ -261,15 +263,80 @@ static int run_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
 // conversion y: P' -> Q whose overflow count is unambiguous (|y| < P'/4).
 //   expand_joint<L,K>   : [p][L][N] -> [p][L+K][N]   (rows 0..L-1 copied through)
 //   contract_joint<L,K> : [p][L+K][N] -> [p][L][N]
+// Second generation of the two kernels (what bounds them is the FMA-heavy pipe, profiles/r01_ncu_bfv_step.txt):
+//   * Garner with the inverse folded into the constants: d_i = (a_i - sum_{j<i} d_j g_ij) ginv_i becomes ONE 128-bit
+//     accumulation  a_i (c ginv_i) + sum_j d_j (-g_ij ginv_i)  and one reduction per digit (no Shoup products);
+//     in the contraction a_i = t x_i + h is folded in as well (t ginv_i, h ginv_i);
+//   * eta_j = (t x'_j + h - r mod p_j) comb_j likewise one accumulation x'_j (t comb_j) + h comb_j + sum_i d_i (-ev_ji comb_j);
+//   * SP = every prime is 2^60 + e, e < 2^28 (the reference's nextprime(2^60+1) chains): 128-bit sums are reduced by two
+//     Solinas folds at bit 60 (3 IMAD.WIDE + 3 IMAD) instead of a Shoup product plus a Barrett step (9 IMAD.WIDE + 6 IMAD).
+__device__ __forceinline__ u64 mulw32(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+// z mod q, canonical; SP: q = 2^60 + e and z < 2^126 (at most 16 products of residues below 2^61)
+template <bool SP>
+__device__ __forceinline__ u64 redj(const u128 z, const PrimeConst& pc, const u32 e) {
+    if (!SP) return red128(z, pc);
+    const u64 M60 = (1ull << 60) - 1;
+    const u64 a0 = (u64)z, a1 = (u64)(z >> 64);
+    const u64 H0 = (a0 >> 60) | (a1 << 4);              // H = z >> 60 = H1 2^64 + H0, H1 < 4
+    const u32 H1 = (u32)(a1 >> 60);
+    const u64 t0 = mulw32((u32)H0, e), t1 = mulw32((u32)(H0 >> 32), e);
+    const u64 mid = t1 + (t0 >> 32);                    // T = H e = Th 2^64 + Tl < 2^94
+    const u64 Tl = (mid << 32) | (u32)t0;
+    const u64 Th = (mid >> 32) + (u64)(H1 * e);
+    const u64 Thi = (Tl >> 60) | (Th << 4);             // T >> 60 < 2^34
+    const u64 U = mulw32((u32)Thi, e) + ((u64)((u32)(Thi >> 32) * e) << 32);   // < 2^62
+    u64 r = (a0 & M60) + (pc.q - (Tl & M60)) + U;       // z = lo - T_lo + T_hi e (mod q); in (0, 6q)
+    r = (r & M60) + pc.q - (u64)((u32)(r >> 60) * e);   // in (0, 2q)
+    return csub(r, pc.q);
+}
+
+template <int LN>
+struct GarnerF {
+    u64 ng[LN > 1 ? tri(LN) : 1];  // ng[tri(i)+j] = -(prod_{k<j} q_k) ginv_i mod q_i, j < i
+    u64 sc[LN];                    // multiplier of the residue: c ginv_i mod q_i
+    u64 ad[LN];                    // constant term: h ginv_i mod q_i
+    u64 half[LN];                  // mixed-radix digits of floor(Q/2)
+    PrimeConst pc[LN];
+    u32 e[LN];                     // q_i - 2^60 (SP)
+};
+// mixed-radix digits of the integer with residues sc^-1-scaled ... : d_i = (c r_i + h - sum_j d_j g_ij) ginv_i
+template <int LN, bool SP, bool ADD>
+__device__ __forceinline__ void garner_fused(const u64 (&r)[LN], u64 (&d)[LN], const GarnerF<LN>& g) {
+#pragma unroll
+    for (int i = 0; i < LN; i++) {
+        u128 a = (u128)r[i] * g.sc[i];
+        if (ADD) a += g.ad[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) a += (u128)d[j] * g.ng[tri(i) + j];
+        d[i] = redj<SP>(a, g.pc[i], g.e[i]);
+    }
+}
+template <int LN>
+__device__ __forceinline__ bool above_half_f(const u64 (&d)[LN], const GarnerF<LN>& g) {
+    bool gt = false, decided = false;
+#pragma unroll
+    for (int i = LN - 1; i >= 0; i--) {
+        const bool ne = d[i] != g.half[i];
+        if (!decided && ne) gt = d[i] > g.half[i];
+        decided = decided || ne;
+    }
+    return gt;
+}
+
 template <int L, int K>
 struct ExpandJTab {
-    GarnerC<L> g;
+    GarnerF<L> g;
     u64 ev[K * L];   // (prod_{m<i} q_m) mod p_j
     u64 qmod[K];     // Q mod p_j
     PrimeConst pcb[K];
+    u32 eb[K];       // p_j - 2^60 (SP)
 };
 
-template <int L, int K>
+template <int L, int K, bool SP>
 __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
                                                            const u64 total, const __grid_constant__ ExpandJTab<L, K> T) {
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,11 +349,14 @@ __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict
         r[i] = in[((p * L + i) << logN) + n];
         out[((p * (L + K) + i) << logN) + n] = r[i];
     }
-    garner_reg<L, L>(r, d, T.g);
-    const bool neg = above_half_reg<L>(d, T.g);
+    garner_fused<L, SP, false>(r, d, T.g);
+    const bool neg = above_half_f<L>(d, T.g);
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        u64 v = eval_reg<L, L>(d, T.ev + j * L, T.pcb[j]);
+        u128 a = 0;
+#pragma unroll
+        for (int i = 0; i < L; i++) a += (u128)d[i] * T.ev[j * L + i];
+        u64 v = redj<SP>(a, T.pcb[j], T.eb[j]);
         if (neg) v = sub_mod(v, T.qmod[j], T.pcb[j].q);
         out[((p * (L + K) + L + j) << logN) + n] = v;
     }
@@ -294,36 +364,30 @@ __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict
 
 template <int L, int K>
 struct ContractJTab {
-    GarnerC<L> gq;
-    tw_t t_q[L];             // t mod q_i
-    u64 h_q[L];              // floor(Q/2) mod q_i
-    u64 ev_qb[K * L];        // (prod_{m<i} q_m) mod p_j
-    tw_t t_b[K];             // t mod p_j
-    u64 h_b[K];              // floor(Q/2) mod p_j
-    tw_t comb[K];            // Q^-1 (P'/p_j)^-1 mod p_j
+    GarnerF<L> gq;           // sc = t ginv_i, ad = floor(Q/2) ginv_i: digits of r = (t x + floor(Q/2)) mod Q
+    u64 xa[K];               // t comb_j mod p_j,  comb_j = Q^-1 (P'/p_j)^-1 mod p_j
+    u64 ha[K];               // floor(Q/2) comb_j mod p_j
+    u64 nev[K * L];          // -(prod_{m<i} q_m) comb_j mod p_j
     PrimeConst pcb[K];
+    u32 eb[K];               // p_j - 2^60 (SP)
     u64 ev_bq[(K + 1) * L];  // [j*L + i] = (P'/p_j) mod q_i, j < K; [K*L + i] = (-P') mod q_i
     u32 sh[K];               // eta_j >> sh_j has at most 32 bits
     u32 R[K];                // floor(2^(58+sh_j) / p_j)
 };
 
-template <int L, int K>
+template <int L, int K, bool SP>
 __global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
                                                              const u64 total, const __grid_constant__ ContractJTab<L, K> T) {
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const u64 p = idx >> logN;
     const u32 n = (u32)(idx & ((1u << logN) - 1));
-    // a = t x + h modulo every q_i; r = a mod Q as mixed-radix digits (exact, non-centred)
-    u64 a[L], d[L];
+    // r = (t x + h) mod Q as mixed-radix digits (exact, non-centred), a_i = t x_i + h folded into the Garner constants
+    u64 x[L], d[L];
 #pragma unroll
-    for (int i = 0; i < L; i++) {
-        const u64 q = T.gq.pc[i].q;
-        const u64 x = in[((p * (L + K) + i) << logN) + n];
-        a[i] = add_mod(shoup_full(x, T.t_q[i].w, T.t_q[i].wp, q), T.h_q[i], q);
-    }
-    garner_reg<L, L>(a, d, T.gq);
-    // y = (a - r) / Q modulo p_j, pre-multiplied by (P'/p_j)^-1 for the CRT sum
+    for (int i = 0; i < L; i++) x[i] = in[((p * (L + K) + i) << logN) + n];
+    garner_fused<L, SP, true>(x, d, T.gq);
+    // y = (t x + h - r) / Q modulo p_j, pre-multiplied by (P'/p_j)^-1 for the CRT sum
     //   y = sum_j eta_j P'/p_j - w P',  w = round(sum_j eta_j / p_j)
     // accumulated on the fly into one 128-bit sum per q_i.  The loop over j is NOT unrolled:
     // fully unrolled the kernel is 68 KB of code and stalls 25% of the time on instruction
@@ -335,11 +399,12 @@ __global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restri
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
         const PrimeConst pc = T.pcb[j];
-        const u64 x = in[((p * (L + K) + L + j) << logN) + n];
-        const tw_t tb = T.t_b[j], cm = T.comb[j];
-        const u64 aj = add_mod(shoup_full(x, tb.w, tb.wp, pc.q), T.h_b[j], pc.q);
-        const u64 rj = eval_reg<L, L>(d, T.ev_qb + j * L, pc);
-        const u64 eta = shoup_full(sub_mod(aj, rj, pc.q), cm.w, cm.wp, pc.q);
+        const u64 xj = in[((p * (L + K) + L + j) << logN) + n];
+        u128 a = (u128)xj * T.xa[j] + T.ha[j];
+        const u64* nv = T.nev + j * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) a += (u128)d[i] * nv[i];
+        const u64 eta = redj<SP>(a, pc, T.eb[j]);
         F += (u64)(u32)(eta >> T.sh[j]) * T.R[j];
         const u64* ev = T.ev_bq + j * L;
 #pragma unroll
@@ -350,7 +415,7 @@ __global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restri
 #pragma unroll
     for (int i = 0; i < L; i++) {
         acc[i] += (u128)w * T.ev_bq[K * L + i];
-        out[((p * L + i) << logN) + n] = red128(acc[i], T.gq.pc[i]);
+        out[((p * L + i) << logN) + n] = redj<SP>(acc[i], T.gq.pc[i], T.gq.e[i]);
     }
 }
 
@@ -375,6 +440,36 @@ static int joint_basis_size(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
     return 0;
 }
 
+static bool is_sp_prime(u64 q) { return (q >> 60) == 1 && q - (1ull << 60) < (1ull << 28); }
+// c = multiplier of the residues (1 or t), h = additive constant (0 or floor(Q/2)), both as values mod each q_i
+template <int LN>
+static void fill_garner_fused(GarnerF<LN>& g, const tfb_ctx* c, u64 mult, bool add_half) {
+    for (int i = 0; i < LN; i++) {
+        const u64 qi = c->q[i];
+        u64 M = 1 % qi;
+        u64 gm[LN > 0 ? LN : 1];
+        for (int j = 0; j < i; j++) {
+            gm[j] = M;
+            M = h_mulmod(M, c->q[j] % qi, qi);
+        }
+        const u64 ginv = i ? h_invmod(M, qi) : 1 % qi;
+        for (int j = 0; j < i; j++) {
+            const u64 v = h_mulmod(gm[j], ginv, qi);
+            g.ng[tri(i) + j] = v ? qi - v : 0;
+        }
+        g.sc[i] = h_mulmod(mult % qi, ginv, qi);
+        g.ad[i] = add_half ? h_mulmod(half_mod(c, qi), ginv, qi) : 0;
+        g.half[i] = c->halfmr[i];
+        g.pc[i] = h_prime_const(qi);
+        g.e[i] = (u32)(qi - (1ull << 60));
+    }
+}
+static bool joint_sp(const tfb_ctx* cq, const tfb_ctx* cb, int K) {
+    for (u32 i = 0; i < cq->L; i++) if (!is_sp_prime(cq->q[i])) return false;
+    for (int j = 0; j < K; j++) if (!is_sp_prime(cb->q[j])) return false;
+    return !g_force_generic_red;
+}
+
 template <int L, int K>
 static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u64 polys, cudaStream_t st) {
     typedef ExpandJTab<L, K> Tab;
@@ -383,17 +478,22 @@ static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u
     auto it = cache.find(key);
     if (it == cache.end()) {
         Tab t;
-        fill_garner<L>(t.g, cq);
+        fill_garner_fused<L>(t.g, cq, 1, false);
         for (int j = 0; j < K; j++) {
             fill_eval(t.ev + j * L, L, cq, cb->q[j], &t.qmod[j]);
             t.pcb[j] = h_prime_const(cb->q[j]);
+            t.eb[j] = (u32)(cb->q[j] - (1ull << 60));
         }
         it = cache.emplace(key, t).first;
     }
     const u64 total = polys * cq->N;
     const unsigned tb = 128;
     const u64 nb = (total + tb - 1) / tb;
-    { ProfScope ps(PC_BASE_SWITCH, st); expand_joint_kernel<L, K><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second); }
+    {
+        ProfScope ps(PC_BASE_SWITCH, st);
+        if (joint_sp(cq, cb, K)) expand_joint_kernel<L, K, true><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
+        else expand_joint_kernel<L, K, false><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
+    }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
@@ -406,11 +506,9 @@ static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u6
     auto it = cache.find(key);
     if (it == cache.end()) {
         Tab T;
-        fill_garner<L>(T.gq, cq);
+        fill_garner_fused<L>(T.gq, cq, t, true);
         for (int i = 0; i < L; i++) {
             const u64 qi = cq->q[i];
-            T.t_q[i] = h_tw(t % qi, qi);
-            T.h_q[i] = half_mod(cq, qi);
             u64 Pm = 1 % qi;   // P' mod q_i
             for (int j = 0; j < K; j++) Pm = h_mulmod(Pm, cb->q[j] % qi, qi);
             for (int j = 0; j < K; j++) {   // (P'/p_j) mod q_i
@@ -422,14 +520,19 @@ static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u6
         }
         for (int j = 0; j < K; j++) {
             const u64 pj = cb->q[j];
-            u64 Qm;
-            fill_eval(T.ev_qb + j * L, L, cq, pj, &Qm);
-            T.t_b[j] = h_tw(t % pj, pj);
-            T.h_b[j] = half_mod(cq, pj);
+            u64 Qm, ev[L];
+            fill_eval(ev, L, cq, pj, &Qm);
             u64 M = 1 % pj;   // (P'/p_j) mod p_j
             for (int m = 0; m < K; m++) if (m != j) M = h_mulmod(M, cb->q[m] % pj, pj);
-            T.comb[j] = h_tw(h_invmod(h_mulmod(Qm, M, pj), pj), pj);
+            const u64 comb = h_invmod(h_mulmod(Qm, M, pj), pj);
+            T.xa[j] = h_mulmod(t % pj, comb, pj);
+            T.ha[j] = h_mulmod(half_mod(cq, pj), comb, pj);
+            for (int i = 0; i < L; i++) {
+                const u64 v = h_mulmod(ev[i], comb, pj);
+                T.nev[j * L + i] = v ? pj - v : 0;
+            }
             T.pcb[j] = h_prime_const(pj);
+            T.eb[j] = (u32)(pj - (1ull << 60));
             const u32 bits = 64 - (u32)__builtin_clzll(pj);
             T.sh[j] = bits > 32 ? bits - 32 : 0;
             T.R[j] = (u32)((((u128)1) << (58 + T.sh[j])) / pj);
@@ -439,7 +542,11 @@ static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u6
     const u64 total = polys * cq->N;
     const unsigned tb = 128;
     const u64 nb = (total + tb - 1) / tb;
-    { ProfScope ps(PC_BFV_CONTRACT, st); contract_joint_kernel<L, K><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second); }
+    {
+        ProfScope ps(PC_BFV_CONTRACT, st);
+        if (joint_sp(cq, cb, K)) contract_joint_kernel<L, K, true><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
+        else contract_joint_kernel<L, K, false><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
+    }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

@@ -65,9 +65,10 @@ def kernel_launches() -> int:
     return int(load_library().tfb_kernel_launches())
 
 
-def force_generic(on: bool) -> None:
-    """testing hook: use the generic base-conversion kernels instead of the specialised ones"""
-    _check(load_library().tfb_debug_force_generic(C.c_int(1 if on else 0)))
+def force_generic(on) -> None:
+    """testing hook: 1/True = generic base-conversion kernels instead of the specialised ones; 2 = specialised kernels
+    with the generic 128-bit reduction instead of the Solinas folds for 2^60 + e primes; 0/False = default"""
+    _check(load_library().tfb_debug_force_generic(C.c_int(int(on))))
 
 
 def ntt_version(v: int) -> None:
