@@ -189,6 +189,8 @@ int tfb_ring_mul_host(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64
 int tfb_ct_tensor_host(tfb_ctx* ctx, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
 int tfb_bfv_mul_host(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream);
 int tfb_rescale_host(tfb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream);
+int tfb_bfv_encode_host(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream);
+int tfb_bfv_decode_host(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
 
 #ifdef __cplusplus
 }

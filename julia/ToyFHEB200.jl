@@ -107,4 +107,27 @@ function bfv_mul(ℛ, ℛbig, t::Integer, c1::Vector{<:RingElement}, c2::Vector{
     [RingElement{ℛ}(OffsetArray(unpack(proto.parent, out[:, :, k]), axes(proto)...), nothing) for k in 1:3]
 end
 
+# BFV plaintext maps (bfv.jl:21-29): Delta * m and mod(divround(SignedMod(x), Delta), t), exact on the device
+limbs(x::Integer) = (n = cld(max(ndigits(x, base=2), 1), 64); UInt64[UInt64((x >> (64 * (i - 1))) & typemax(UInt64)) for i in 1:n])
+
+function bfv_encode(ℛ, t::Integer, Δ::Integer, m::Vector{UInt64})
+    d = limbs(Δ)
+    L = length(ℛ.ψ.c)                                   # number of RNS primes (crt.jl:293)
+    out = Matrix{UInt64}(undef, length(m), L)
+    check(ccall((:tfb_bfv_encode_host, LIB), Cint,
+                (Ptr{Cvoid}, UInt64, Ptr{UInt64}, UInt32, Ptr{UInt64}, Ptr{UInt64}, UInt64, Ptr{Cvoid}),
+                context(ℛ), UInt64(t), d, length(d), m, out, 1, C_NULL))
+    out
+end
+
+function bfv_decode(ℛ, t::Integer, Δ::Integer, b::RingElement)
+    d = limbs(Δ)
+    buf = pack(coeffs_primal(b).parent)
+    out = Vector{UInt64}(undef, size(buf, 1))
+    check(ccall((:tfb_bfv_decode_host, LIB), Cint,
+                (Ptr{Cvoid}, UInt64, Ptr{UInt64}, UInt32, Ptr{UInt64}, Ptr{UInt64}, UInt64, Ptr{Cvoid}),
+                context(ℛ), UInt64(t), d, length(d), buf, out, 1, C_NULL))
+    out
+end
+
 end # module

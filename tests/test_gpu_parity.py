@@ -282,6 +282,15 @@ def test_bfv_encode_decode(N, logqs, t):
             assert np.array_equal(back, m % np.uint64(t))
     with pytest.raises(T.EngineError):
         ctx.bfv_decode(t, 1, ctx.to_device(_to_rns([0] * N, qs)[None]))          # Delta far too small for a word-size quotient
+    # host-buffer variants: same results from numpy buffers
+    delta = Q // t
+    m = rng.integers(0, t, size=(2, N), dtype=np.uint64)
+    enc = np.empty((2, len(qs), N), dtype=np.uint64)
+    ctx.bfv_encode_host(t, delta, m, enc)
+    assert np.array_equal(enc, H(ctx.bfv_encode(t, delta, ctx.to_device(m))))
+    dec = np.empty((2, N), dtype=np.uint64)
+    ctx.bfv_decode_host(t, delta, enc, dec)
+    assert np.array_equal(dec, m)
 
 
 # --------------------------------------------------------------------- key switching

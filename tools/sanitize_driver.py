@@ -1,0 +1,43 @@
+"""Small driver for compute-sanitizer (memcheck / racecheck): a few rows through every NTT kernel family and
+one small BFV multiply, keyswitch and rescale; results checked against the oracle."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import toyfhe_b200 as T
+from oracle import c_oracle as CO
+
+def rnd(rng, qs, shape, N):
+    out = np.empty(shape + (len(qs), N), dtype=np.uint64)
+    for i, q in enumerate(qs):
+        out[..., i, :] = rng.integers(0, q, size=shape + (N,), dtype=np.uint64)
+    return out
+
+rng = np.random.default_rng(0)
+H = T.Context.to_host
+for logN, logqs, B, pair in ((14, [60, 60], 100, False), (13, [60, 40], 200, False), (12, [50], 700, False), (15, [60, 40], 90, False),
+                             (15, [60, 40], 90, True), (10, [60], 3, False), (5, [40], 3, False)):
+    N = 1 << logN
+    qs, psis = T.prime_chain(N, sorted(logqs))
+    ctx, orc = T.Context(N, qs, psis), CO.Rns(N, qs, psis)
+    a = rnd(rng, qs, (B,), N)
+    T.ntt_pair(pair)
+    d = ctx.to_device(a)
+    f = ctx.ntt_fwd(d)
+    back = ctx.ntt_inv(f)
+    T.ntt_pair(False)
+    assert np.array_equal(H(f[:2]), orc.nntt(a[:2])) and np.array_equal(H(back), a), (logN, pair)
+    print("ntt ok", logN, logqs, "pair" if pair else "", flush=True)
+N, L, Lb, t = 1024, 8, 17, 65537
+allq, allpsi = T.prime_chain(N, [60] * (L + Lb))
+cq, cb = T.Context(N, allq[:L], allpsi[:L]), T.Context(N, allq[L:], allpsi[L:])
+c1, c2 = rnd(rng, allq[:L], (3, 2), N), rnd(rng, allq[:L], (3, 2), N)
+got = H(cq.bfv_mul(cb, t, cq.to_device(c1), cq.to_device(c2)))
+assert np.array_equal(got, CO.bfv_mul(CO.Rns(N, allq[:L], allpsi[:L]), CO.Rns(N, allq[L:], allpsi[L:]), t, c1, c2))
+print("bfv_mul ok", flush=True)
+D = T.ndigits(allq[:L], 2)
+key = cq.ntt_fwd(cq.to_device(rnd(rng, allq[:L], (D, 2), N)))
+ks = cq.keyswitch(key, cq.to_device(rnd(rng, allq[:L], (2, 3), N)), 2)
+rs = cq.rescale(cq.to_device(c1))
+torch.cuda.synchronize()
+print("keyswitch / rescale ran", flush=True)

@@ -838,6 +838,36 @@ int tfb_rescale_host(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t pol
     TFB_CUDA(cudaStreamSynchronize(st));
     return TFB_OK;
 }
+int tfb_bfv_encode_host(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(delta); CHECK_PTR(m); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pin = (size_t)c->N, pout = (size_t)c->L * c->N;
+    u64* d;
+    int rc = io_buf(c, polys * (pin + pout), &d);
+    if (rc) return rc;
+    H2D(d, m, polys * pin);
+    if ((rc = launch_bfv_encode(c, t, delta, nl, d, d + polys * pin, polys, st))) return rc;
+    D2H(out, d + polys * pin, polys * pout);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
+int tfb_bfv_decode_host(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(delta); CHECK_PTR(b); CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pin = (size_t)c->L * c->N, pout = (size_t)c->N;
+    u64* d;
+    int rc = io_buf(c, polys * (pin + pout), &d);
+    if (rc) return rc;
+    H2D(d, b, polys * pin);
+    if ((rc = launch_bfv_decode(c, t, delta, nl, d, d + polys * pin, polys, st))) return rc;
+    D2H(out, d + polys * pin, polys * pout);
+    TFB_CUDA(cudaStreamSynchronize(st));
+    return TFB_OK;
+}
 
 }  // extern "C"
 

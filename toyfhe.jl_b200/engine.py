@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
-    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_bfv_encode", "tfb_bfv_decode",
+    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
     "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
     "tfb_bfv_mul_host", "tfb_rescale_host",
 ]
@@ -351,6 +351,17 @@ class Context:
     def bfv_mul_host(self, big: "Context", t: int, c1, c2, out, stream=None):
         _check(self._lib.tfb_bfv_mul_host(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out),
                                           C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream)))
+        return out
+
+    def bfv_encode_host(self, t: int, delta: int, m, out, stream=None):
+        arr, n = self._limbs(delta)
+        polys = int((m.numel() if hasattr(m, "numel") else m.size) // self.N)
+        _check(self._lib.tfb_bfv_encode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream)))
+        return out
+
+    def bfv_decode_host(self, t: int, delta: int, b, out, stream=None):
+        arr, n = self._limbs(delta)
+        _check(self._lib.tfb_bfv_decode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
         return out
 
     def rescale_host(self, a, out, stream=None):
