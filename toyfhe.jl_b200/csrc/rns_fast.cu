@@ -270,28 +270,11 @@ static int run_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
 //   * eta_j = (t x'_j + h - r mod p_j) comb_j likewise one accumulation x'_j (t comb_j) + h comb_j + sum_i d_i (-ev_ji comb_j);
 //   * SP = every prime is 2^60 + e, e < 2^28 (the reference's nextprime(2^60+1) chains): 128-bit sums are reduced by two
 //     Solinas folds at bit 60 (3 IMAD.WIDE + 3 IMAD) instead of a Shoup product plus a Barrett step (9 IMAD.WIDE + 6 IMAD).
-__device__ __forceinline__ u64 mulw32(u32 a, u32 b) {
-    u64 r;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
-    return r;
-}
 // z mod q, canonical; SP: q = 2^60 + e and z < 2^126 (at most 16 products of residues below 2^61)
 template <bool SP>
 __device__ __forceinline__ u64 redj(const u128 z, const PrimeConst& pc, const u32 e) {
     if (!SP) return red128(z, pc);
-    const u64 M60 = (1ull << 60) - 1;
-    const u64 a0 = (u64)z, a1 = (u64)(z >> 64);
-    const u64 H0 = (a0 >> 60) | (a1 << 4);              // H = z >> 60 = H1 2^64 + H0, H1 < 4
-    const u32 H1 = (u32)(a1 >> 60);
-    const u64 t0 = mulw32((u32)H0, e), t1 = mulw32((u32)(H0 >> 32), e);
-    const u64 mid = t1 + (t0 >> 32);                    // T = H e = Th 2^64 + Tl < 2^94
-    const u64 Tl = (mid << 32) | (u32)t0;
-    const u64 Th = (mid >> 32) + (u64)(H1 * e);
-    const u64 Thi = (Tl >> 60) | (Th << 4);             // T >> 60 < 2^34
-    const u64 U = mulw32((u32)Thi, e) + ((u64)((u32)(Thi >> 32) * e) << 32);   // < 2^62
-    u64 r = (a0 & M60) + (pc.q - (Tl & M60)) + U;       // z = lo - T_lo + T_hi e (mod q); in (0, 6q)
-    r = (r & M60) + pc.q - (u64)((u32)(r >> 60) * e);   // in (0, 2q)
-    return csub(r, pc.q);
+    return red126_sp60((u64)(z >> 64), (u64)z, pc.q, e);
 }
 
 template <int LN>

@@ -129,6 +129,12 @@ int launch_scalar_mul(tfb_ctx* c, const u64* a, const u64* s_host, u64* out, u64
 // ---------------------------------------------------- ciphertext tensor (dual)
 // a,b: [B][2][L][N] (NTT domain) -> out [B][3][L][N]: d0=a0 b0, d1=a0 b1+a1 b0, d2=a1 b1
 // (the coefficient-wise body of rlwe_she.jl:255-258 once everything is in dual form)
+// SP: every prime is 2^60 + e (e < 2^28): products and the two-term sum are reduced by Solinas folds (red126_sp60)
+template <bool SP>
+__device__ __forceinline__ u64 tensor_red(const acc128 s, const PrimeConst& pc) {
+    return SP ? red126_sp60(s.hi, s.lo, pc.q, (u32)(pc.q - (1ull << 60))) : red128_full(s, pc);
+}
+template <bool SP>
 __global__ void tensor_dual_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ b,
                                    ulonglong2* __restrict__ out, const PrimeParams* __restrict__ pp, const u32 L,
                                    const u32 logN, const u64 total2) {
@@ -141,18 +147,25 @@ __global__ void tensor_dual_kernel(const ulonglong2* __restrict__ a, const ulong
         const u64 ia0 = ((bi * 2 + 0) * L + pi) * rowlen + n2, ia1 = ((bi * 2 + 1) * L + pi) * rowlen + n2;
         const ulonglong2 a0 = a[ia0], a1 = a[ia1], b0 = b[ia0], b1 = b[ia1];
         ulonglong2 d0, d1, d2;
-        d0.x = barrett_mul(a0.x, b0.x, pc);
-        d0.y = barrett_mul(a0.y, b0.y, pc);
-        d2.x = barrett_mul(a1.x, b1.x, pc);
-        d2.y = barrett_mul(a1.y, b1.y, pc);
         acc128 s = {0, 0};
+        if (SP) {
+            mac128(s, a0.x, b0.x); d0.x = tensor_red<SP>(s, pc); s.lo = s.hi = 0;
+            mac128(s, a0.y, b0.y); d0.y = tensor_red<SP>(s, pc); s.lo = s.hi = 0;
+            mac128(s, a1.x, b1.x); d2.x = tensor_red<SP>(s, pc); s.lo = s.hi = 0;
+            mac128(s, a1.y, b1.y); d2.y = tensor_red<SP>(s, pc); s.lo = s.hi = 0;
+        } else {
+            d0.x = barrett_mul(a0.x, b0.x, pc);
+            d0.y = barrett_mul(a0.y, b0.y, pc);
+            d2.x = barrett_mul(a1.x, b1.x, pc);
+            d2.y = barrett_mul(a1.y, b1.y, pc);
+        }
         mac128(s, a0.x, b1.x);
         mac128(s, a1.x, b0.x);
-        d1.x = red128_full(s, pc);
+        d1.x = tensor_red<SP>(s, pc);
         s.lo = s.hi = 0;
         mac128(s, a0.y, b1.y);
         mac128(s, a1.y, b0.y);
-        d1.y = red128_full(s, pc);
+        d1.y = tensor_red<SP>(s, pc);
         out[((bi * 3 + 0) * L + pi) * rowlen + n2] = d0;
         out[((bi * 3 + 1) * L + pi) * rowlen + n2] = d1;
         out[((bi * 3 + 2) * L + pi) * rowlen + n2] = d2;
@@ -163,7 +176,14 @@ int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 bat
     if (!batch) return TFB_OK;
     const u64 total2 = batch * c->L * c->N / 2;
     const unsigned tb = 256, nb = grid_for(total2, tb);
-    { ProfScope ps(PC_TENSOR, st); tensor_dual_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    {
+        extern bool g_force_generic_red;
+        ProfScope ps(PC_TENSOR, st);
+        if (c->ntt_mode == 2 && !g_force_generic_red)   // every prime 2^60 + e, e < 2^28
+            tensor_dual_kernel<true><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2);
+        else
+            tensor_dual_kernel<false><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2);
+    }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
