@@ -236,6 +236,44 @@ def test_ckks_ct_mul_and_rescale():
     assert np.allclose(dec.data, a.data * b.data, atol=1e-4)
 
 
+def _mnist_style_ring(N, n40):
+    """examples/encrypted_mnist/infer.jl:97-110: (q0 60-bit, n40 x 40-bit, special 60-bit), primes found the same way"""
+    q0 = O.nextprime(2 ** 60 + 1, 2 * N)
+    ps = O.nextprime(q0 + 2 * N, 2 * N)
+    qs = [O.nextprime(2 ** 40 + 1, 2 * N)]
+    for _ in range(n40 - 1):
+        qs.append(O.nextprime(qs[-1] + 2 * N, 2 * N))
+    return T.NegacyclicRing(N, qs=[q0] + qs + [ps])
+
+
+@pytest.mark.parametrize("logN,n40", [(13, 5), (15, 9)])
+def test_ckks_full_size_rotate_multiply_rescale(logN, n40):
+    """BASELINE configs 5 and 3 at their full sizes (N = 2^13 with 7 primes; N = 2^15 with a 10-level chain + special
+    prime, ModulusRaised CRT-digit keyswitch as in examples/encrypted_mnist/infer.jl:110): encrypt, rotate with a
+    GaloisKey, multiply by a plaintext vector, rescale, decrypt -- the decrypted slots equal the plaintext computation
+    (the size-independent property the reference's own CKKS tests check, test/ckks_rotate.jl, ckks_matmul.jl,
+    ckks_modswitch.jl)"""
+    N = 1 << logN
+    R = _mnist_style_ring(N, n40)
+    params = T.ModulusRaised(T.CKKSParams(R, 0, 3.2))
+    s = T.Sampler(100 + logN)
+    kp = T.keygen(s, params)
+    scale = 2.0 ** 40
+    rng = np.random.default_rng(logN)
+    v = rng.uniform(-1, 1, N // 2)
+    w = rng.uniform(-2, 2, N // 2)
+    c = T.encrypt(s, kp, T.CKKSEncoding(scale, v.astype(np.complex128)))
+    assert c.ring().L == n40 + 1                       # special prime dropped from the ciphertext ring
+    gk = T.keygen_galois(s, kp.priv, steps=1)
+    rot = T.rotate(gk, c)
+    tol = 1e-6 if logN == 13 else 3e-5              # fresh + keyswitch noise grows with N at a fixed scale of 2^40
+    assert np.allclose(np.real(T.decrypt(kp, rot).data), np.roll(v, 1), atol=tol)
+    prod = T.modswitch(T.ckks_mul_plain_vector(w, rot))  # scale^2 / q_last ~ 2^40
+    assert prod.ring().L == n40
+    got = np.real(T.decrypt(kp, prod).data)
+    assert np.allclose(got, w * np.roll(v, 1), atol=10 * tol)
+
+
 # ------------------------------------------ ciphertext-level bit-exact parity vs the oracle
 def test_scheme_bit_exact_vs_oracle():
     N = 64

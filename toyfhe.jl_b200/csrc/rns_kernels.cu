@@ -50,6 +50,10 @@ __global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2*
         } else if (OP == 1) {
             r.x = sub_mod(x.x, y.x, pc.q);
             r.y = sub_mod(x.y, y.y, pc.q);
+        } else if (OP == 3) {   // product on 2^60 + e primes: full product + Solinas folds (modarith.cuh red126_sp60)
+            const u32 e = (u32)(pc.q - (1ull << 60));
+            r.x = red126_sp60(__umul64hi(x.x, y.x), x.x * y.x, pc.q, e);
+            r.y = red126_sp60(__umul64hi(x.y, y.y), x.y * y.y, pc.q, e);
         } else {
             r.x = barrett_mul(x.x, y.x, pc);
             r.y = barrett_mul(x.y, y.y, pc);
@@ -101,6 +105,7 @@ int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 r
     const unsigned tb = 256, nb = grid_for(total2, tb);
     if (op == 0) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<0><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
     else if (op == 1) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<1><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    else if (c->ntt_mode == 2 && !g_force_generic) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<3><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
     else { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<2><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
