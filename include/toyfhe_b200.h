@@ -152,6 +152,17 @@ int tfb_bfv_mul(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1
 int tfb_bfv_encode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream);
 int tfb_bfv_decode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
 
+/* ---- sampling on the device ------------------------------
+ * RingSampler (poly.jl:7-23) for keygen / encrypt (rlwe_she.jl:155-195).  The reference's RNG is Julia's unseeded
+ * global one, so parity with it is statistical only; these are counter-based (Philox4x32-10, key = seed, counter =
+ * (position, stream, attempt)): reproducible, independent of launch geometry, restated bit for bit on the CPU by
+ * oracle/sampler_oracle.py.
+ * uniform:  out [polys][L][N], every residue independent and uniform in [0, q_i) (crt.jl:146-148, 277-279).
+ * gaussian: out [polys][L][N], x = round(sigma z), z ~ N(0,1) (Box-Muller), the same integer under every prime
+ *           (DiscreteNormal(0, sigma): bfv.jl:31-32, ckks.jl:24-25). */
+int tfb_sample_uniform(tfb_ctx* ctx, uint64_t seed, uint32_t stream_id, uint64_t* out, uint64_t polys, void* stream);
+int tfb_sample_gaussian(tfb_ctx* ctx, double sigma, uint64_t seed, uint32_t stream_id, uint64_t* out, uint64_t polys, void* stream);
+
 /* ---- key switching ------------------------------------------------------------ */
 /* Digit polynomials of keyswitch (rlwe_she.jl:326-338).  cend = last ciphertext
  * component [batch][L][N] (primal, contiguous); relin_window w == 0 -> CRT digits

@@ -247,6 +247,39 @@ def test_bfv_mul_joint_basis_extreme_residues():
     assert np.array_equal(got, want)
 
 
+# --------------------------------------------------------------------- sampling on the device (poly.jl:7-23)
+def test_device_sampler_matches_its_cpu_restatement_and_the_distributions():
+    """tfb_sample_uniform / tfb_sample_gaussian vs oracle/sampler_oracle.py (same Philox counters): uniform residues
+    bit-exact (integer path, including the rejection step that removes modulo bias -- 1 draw in 16 is rejected at
+    q ~ 2^60), rounded Gaussian equal up to libm ulps; ranges, reproducibility, stream independence, moments"""
+    from oracle import sampler_oracle as SO
+    N = 1024
+    qs, psis, ctx, _ = _ring(N, [60, 60, 40])
+    seed = 0x1234567890ABCDEF
+    got = H(ctx.sample_uniform(seed, 7, (3,)))
+    assert np.array_equal(got, SO.sample_uniform(seed, 7, 3, qs, N))
+    for i, q in enumerate(qs):
+        assert got[:, i, :].max() < q
+    assert np.array_equal(got, H(ctx.sample_uniform(seed, 7, (3,))))                 # pure function of (seed, stream, position)
+    assert not np.array_equal(got, H(ctx.sample_uniform(seed, 8, (3,))))
+    assert not np.array_equal(got, H(ctx.sample_uniform(seed + 1, 7, (3,))))
+    big = H(ctx.sample_uniform(seed, 9, (64,)))[:, 0, :].astype(np.float64) / qs[0]   # 65536 draws: 16 equal buckets
+    counts = np.histogram(big, bins=16, range=(0.0, 1.0))[0]
+    assert abs(big.mean() - 0.5) < 0.01 and counts.min() > 3700 and counts.max() < 4500
+    sigma = 3.2
+    g = H(ctx.sample_gaussian(sigma, seed, 11, (16,)))
+    want = SO.sample_gaussian(sigma, seed, 11, 16, qs, N)
+    assert (g != want).mean() < 1e-5
+    x = g[:, 0, :].astype(np.int64)
+    x = np.where(x > qs[0] // 2, x - qs[0], x)                                      # centred lift
+    for i, q in enumerate(qs):                                                        # the same integer under every prime
+        xi = g[:, i, :].astype(np.int64)
+        assert np.array_equal(np.where(xi > q // 2, xi - q, xi), x)
+    assert abs(x.mean()) < 0.1 and abs(x.std() - np.sqrt(sigma ** 2 + 1 / 12)) < 0.1 and np.abs(x).max() < 8 * sigma
+    with pytest.raises(T.EngineError):
+        ctx.sample_gaussian(-1.0, seed, 0)
+
+
 # --------------------------------------------------------------------- BFV plaintext maps (bfv.jl:21-29)
 def _to_rns(xs, qs):
     return np.array([[x % q for x in xs] for q in qs], dtype=np.uint64)

@@ -87,6 +87,21 @@ def test_bfv_simd_replay():
     assert got == [int(x) * int(y) % t for x, y in zip(a, b)]
 
 
+def test_bfv_crt_replay_with_device_sampler():
+    """test/bfv_crt.jl with every random draw of keygen / encrypt made on the device (tfb_sample_*): nothing but the
+    6 and the decrypted 36 crosses the host boundary"""
+    n, R, Rbig, params = _bfv_crt_params()
+    s = T.Sampler(77, device=True)
+    kp = T.keygen(s, params)
+    plain = [0] * n
+    plain[0] = 6
+    c = T.encrypt(s, kp, plain)
+    assert T.decrypt(kp, c)[0] == 6
+    assert T.decrypt(kp, c * c)[0] == 36
+    ek = T.keygen_evalmult(s, kp.priv)
+    assert T.decrypt(kp, T.keyswitch(ek, c * c))[0] == 36
+
+
 def test_bfv_keyswitch_replay():
     """test/bfv_keyswitch.jl semantics on the RNS route: relinearise c*c with an
     EvalMultKey (relin_window = 1, base-2 digits), then multiply again"""

@@ -469,6 +469,19 @@ int tfb_bfv_decode(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, c
     return launch_bfv_decode(c, t, delta, nl, b, out, polys, (cudaStream_t)stream);
 }
 
+int tfb_sample_uniform(tfb_ctx* c, uint64_t seed, uint32_t stream_id, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(out);
+    return launch_sample_uniform(c, seed, stream_id, out, polys, (cudaStream_t)stream);
+}
+int tfb_sample_gaussian(tfb_ctx* c, double sigma, uint64_t seed, uint32_t stream_id, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(out);
+    return launch_sample_gaussian(c, sigma, seed, stream_id, out, polys, (cudaStream_t)stream);
+}
+
 // batch chunk so that the R_big intermediates (7 polys per pair) stay bounded
 static u64 bfv_chunk(const tfb_ctx* cb, u64 batch) {
     const size_t per = 7 * (size_t)cb->L * cb->N * sizeof(u64);

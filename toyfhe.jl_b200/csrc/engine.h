@@ -91,6 +91,9 @@ int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, 
 int launch_bfv_encode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* m, u64* out, u64 polys, cudaStream_t st);
 int launch_bfv_decode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int build_garner(tfb_ctx* c);
+// sample_kernels.cu
+int launch_sample_uniform(tfb_ctx* c, u64 seed, u32 stream, u64* out, u64 polys, cudaStream_t st);
+int launch_sample_gaussian(tfb_ctx* c, double sigma, u64 seed, u32 stream, u64* out, u64 polys, cudaStream_t st);
 // rns_fast.cu: specialised register-resident conversions; return false if no specialisation fits
 bool fast_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
 bool fast_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);

@@ -26,11 +26,22 @@ class UsageError(Exception):
 # unseeded global RNG; here the sampler is explicit and seedable.
 # ----------------------------------------------------------------------------
 class Sampler:
-    def __init__(self, seed: int):
+    """device=True draws on the GPU (tfb_sample_uniform / tfb_sample_gaussian, counter-based Philox keyed by the seed;
+    every call takes the next stream id), so keygen and encrypt never touch host memory; device=False is the numpy
+    PCG64 sampler the bit-exact scheme tests share with the oracle."""
+
+    def __init__(self, seed: int, device: bool = False):
         self.rng = np.random.Generator(np.random.PCG64(seed))
+        self.seed, self.device, self._stream = int(seed), bool(device), 0
+
+    def _next_stream(self) -> int:
+        self._stream += 1
+        return self._stream
 
     def uniform(self, ring: NegacyclicRing) -> RingElement:
         """RingSampler(R, DiscreteUniform): every residue drawn independently (crt.jl:146-148)"""
+        if self.device:
+            return RingElement(ring, primal=ring.ctx.sample_uniform(self.seed, self._next_stream())[0])
         a = np.empty((ring.L, ring.N), dtype=np.uint64)
         for i, q in enumerate(ring.qs):
             a[i] = self.rng.integers(0, q, size=ring.N, dtype=np.uint64)
@@ -41,6 +52,8 @@ class Sampler:
 
     def gaussian(self, ring: NegacyclicRing, sigma: float) -> RingElement:
         """RingSampler(R, DiscreteNormal(0, sigma)) (bfv.jl:31-32, ckks.jl:24-25)"""
+        if self.device:
+            return RingElement(ring, primal=ring.ctx.sample_gaussian(sigma, self.seed, self._next_stream())[0])
         return ring(self.gaussian_ints(ring.N, sigma))
 
     def zero(self, ring: NegacyclicRing) -> RingElement:
