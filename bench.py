@@ -325,7 +325,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * 2 * L_Q * Nb),
                 "d2h_bytes_per_step": int(Be * 3 * L_Q * Nb), "batch": Be, "ms_per_step": e2e_s * 1e3,
-                "api": "tfb_bfv_mul_host (pinned host buffers; H2D, kernels and D2H pipelined over 8-pair chunks on three streams)"},
+                "api": "tfb_bfv_mul_host (pinned host buffers; H2D, kernels and D2H pipelined over 8-pair chunks on three streams)",
+                "bound": "PCIe Gen5 x16: 43.9 GB/s per direction with both directions busy (tools/pcie_probe.py, profiles/r01_pcie.txt); "
+                         "4 MiB in + 3 MiB out per pair => ~11.0k pairs/s per GPU link"},
         "roofline": roofline,
         "kernels": kernels,
         "ntt_fwd": {"value": world * ntt_polys / (ntt_ms * 1e-3), "unit": "RNS-NTT/s (N=2^14, L=8)",

@@ -14,10 +14,14 @@
 // primes of the big basis (host picks the smallest KB with prod_{j<KB} p_j above
 // that bound; the Garner tables of a prefix basis are prefixes of the full ones).
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "engine.h"
 
+// the per-(context pair) constant tables below are process-wide caches: distinct contexts may be used from different
+// host threads (include/toyfhe_b200.h "Threading"), so every lookup/insert holds this lock
+static std::mutex g_fast_mu;
 bool g_force_generic_red = false;  // testing hook: Shoup/Barrett reductions even on 2^60 + e primes
 
 __device__ __forceinline__ u64 red128(u128 a, const PrimeConst& pc) {
@@ -198,6 +202,7 @@ template <int LF, int LT>
 static int run_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st) {
     typedef SwitchTab<LF, LT> Tab;
     static std::map<std::pair<u64, u64>, Tab> cache;  // keyed by context uids (never reused)
+    std::lock_guard<std::mutex> lk(g_fast_mu);
     auto key = std::make_pair(from->uid, to->uid);
     auto it = cache.find(key);
     if (it == cache.end()) {
@@ -221,6 +226,7 @@ template <int L, int LB, int KB>
 static int run_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
     typedef ContractTab<L, LB, KB> Tab;
     static std::map<std::tuple<u64, u64, u64>, Tab> cache;  // keyed by context uids (never reused)
+    std::lock_guard<std::mutex> lk(g_fast_mu);
     auto key = std::make_tuple(cq->uid, cb->uid, t);
     auto it = cache.find(key);
     if (it == cache.end()) {
@@ -457,6 +463,7 @@ template <int L, int K>
 static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u64 polys, cudaStream_t st) {
     typedef ExpandJTab<L, K> Tab;
     static std::map<std::pair<u64, u64>, Tab> cache;
+    std::lock_guard<std::mutex> lk(g_fast_mu);
     auto key = std::make_pair(cq->uid, cb->uid);
     auto it = cache.find(key);
     if (it == cache.end()) {
@@ -485,6 +492,7 @@ template <int L, int K>
 static int run_contract_joint(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
     typedef ContractJTab<L, K> Tab;
     static std::map<std::tuple<u64, u64, u64>, Tab> cache;
+    std::lock_guard<std::mutex> lk(g_fast_mu);
     auto key = std::make_tuple(cq->uid, cb->uid, t);
     auto it = cache.find(key);
     if (it == cache.end()) {

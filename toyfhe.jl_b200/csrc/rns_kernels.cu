@@ -12,6 +12,7 @@
 //
 // Layout everywhere: u64 [..][L][N], thread index runs along N (coalesced).
 #include <map>
+#include <mutex>
 
 #include "engine.h"
 
@@ -382,8 +383,10 @@ struct PairKey {
     bool operator<(const PairKey& o) const { return a < o.a || (a == o.a && b < o.b); }
 };
 static std::map<PairKey, PairTab> g_pairs;
+static std::mutex g_pairs_mu;   // contexts may be used from different host threads
 
 void tfb_forget_ctx_pairs(const tfb_ctx* c) {
+    std::lock_guard<std::mutex> lk(g_pairs_mu);
     for (auto it = g_pairs.begin(); it != g_pairs.end();) {
         if (it->first.a == c || it->first.b == c) {
             cudaFree(it->second.ev);
@@ -395,6 +398,7 @@ void tfb_forget_ctx_pairs(const tfb_ctx* c) {
 }
 
 static int get_pair(const tfb_ctx* from, const tfb_ctx* to, PairTab* out) {
+    std::lock_guard<std::mutex> lk(g_pairs_mu);
     PairKey k{from, to};
     auto it = g_pairs.find(k);
     if (it != g_pairs.end()) { *out = it->second; return TFB_OK; }
@@ -645,10 +649,75 @@ int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct
 // acc [B][2][L][N] (dual): acc[b][0] (+)= sum_k masked_k . p_k ; acc[b][1] (+)= sum_k mask_k . p_k
 // dig [B][Dn][L][N] dual; key [D][2][L][N] dual, component 0 = mask, 1 = masked; uses
 // key digits k0 .. k0+Dn-1.
-__global__ void ks_accum_kernel(const u64* __restrict__ dig, const u64* __restrict__ key, u64* __restrict__ acc,
+// The sums are kept as 128-bit integers and reduced only when `cap` more products could overflow (cap =
+// floor(2^128 / qmax^2) - 1: 254 terms for 60-bit primes); the digit loop runs in groups of 4 with all 12 loads of a
+// group issued before its multiply-accumulates (the kernel streams the key and the digit rows once: memory-level
+// parallelism, not arithmetic, bounds it); each thread owns two adjacent coefficients so every access is 128 bits wide.
+__global__ void ks_accum_kernel(const ulonglong2* __restrict__ dig, const ulonglong2* __restrict__ key, ulonglong2* __restrict__ acc,
                                 const u32 L, const u32 logN, const u32 k0, const u32 Dn, const int accumulate,
-                                const PrimeParams* __restrict__ pp, const u64 total) {
+                                const PrimeParams* __restrict__ pp, const u64 total2, const u32 cap) {
+    constexpr u32 U = 4;
+    const u32 lg2 = logN - 1;                    // rows in units of two coefficients (128-bit accesses)
+    const u64 kstride = (u64)L << lg2;           // between consecutive digit rows of one (b, i) and between key components
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 n2 = idx & ((1ull << lg2) - 1);
+        const u64 r = idx >> lg2;  // (b, i)
+        const u64 b = r / L;
+        const u32 i = (u32)(r % L);
+        const PrimeConst pc = pp[i].pc;
+        acc128 a1x = {0, 0}, a1y = {0, 0}, a2x = {0, 0}, a2y = {0, 0};
+        ulonglong2* o1 = acc + (((b * 2 + 0) * L + i) << lg2) + n2;
+        ulonglong2* o2 = acc + (((b * 2 + 1) * L + i) << lg2) + n2;
+        if (accumulate) {
+            const ulonglong2 v1 = *o1, v2 = *o2;
+            a1x.lo = v1.x; a1y.lo = v1.y; a2x.lo = v2.x; a2y.lo = v2.y;
+        }
+        const ulonglong2* dp = dig + (((b * Dn) * L + i) << lg2) + n2;
+        const ulonglong2* kp = key + ((((u64)k0 * 2) * L + i) << lg2) + n2;
+        u32 pending = 0, kk = 0;
+#define KS_REDUCE()                                                                     \
+        do {                                                                            \
+            a1x.lo = red128_full(a1x, pc); a1x.hi = 0; a1y.lo = red128_full(a1y, pc); a1y.hi = 0; \
+            a2x.lo = red128_full(a2x, pc); a2x.hi = 0; a2y.lo = red128_full(a2y, pc); a2y.hi = 0; \
+            pending = 0;                                                                \
+        } while (0)
+        for (; kk + U <= Dn; kk += U) {
+            if (pending + U > cap) KS_REDUCE();
+            ulonglong2 p[U], km[U], kd[U];
+#pragma unroll
+            for (u32 u = 0; u < U; u++) {
+                p[u] = dp[(u64)(kk + u) * kstride];
+                km[u] = kp[(u64)(kk + u) * 2 * kstride];
+                kd[u] = kp[(u64)(kk + u) * 2 * kstride + kstride];
+            }
+#pragma unroll
+            for (u32 u = 0; u < U; u++) {
+                mac128(a1x, kd[u].x, p[u].x); mac128(a1y, kd[u].y, p[u].y);
+                mac128(a2x, km[u].x, p[u].x); mac128(a2y, km[u].y, p[u].y);
+            }
+            pending += U;
+        }
+        for (; kk < Dn; kk++) {
+            if (pending + 1 > cap) KS_REDUCE();
+            const ulonglong2 p = dp[(u64)kk * kstride];
+            const ulonglong2 kd = kp[(u64)kk * 2 * kstride + kstride], km = kp[(u64)kk * 2 * kstride];
+            mac128(a1x, kd.x, p.x); mac128(a1y, kd.y, p.y);
+            mac128(a2x, km.x, p.x); mac128(a2y, km.y, p.y);
+            pending++;
+        }
+#undef KS_REDUCE
+        *o1 = make_ulonglong2(red128_full(a1x, pc), red128_full(a1y, pc));
+        *o2 = make_ulonglong2(red128_full(a2x, pc), red128_full(a2y, pc));
+    }
+}
+
+// scalar variant (one coefficient per thread, groups of 8): more threads, used when the batch is small
+__global__ void ks_accum1_kernel(const u64* __restrict__ dig, const u64* __restrict__ key, u64* __restrict__ acc,
+                                 const u32 L, const u32 logN, const u32 k0, const u32 Dn, const int accumulate,
+                                 const PrimeParams* __restrict__ pp, const u64 total, const u32 cap) {
+    constexpr u32 U = 8;
     const u32 N = 1u << logN;
+    const u64 kstride = (u64)L << logN;
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (b, i)
@@ -662,18 +731,39 @@ __global__ void ks_accum_kernel(const u64* __restrict__ dig, const u64* __restri
             a1.lo = *o1;
             a2.lo = *o2;
         }
-        for (u32 kk = 0; kk < Dn; kk++) {
-            const u64 p = dig[(((b * Dn + kk) * L + i) << logN) + n];
-            const u64 km = key[((((u64)(k0 + kk) * 2 + 0) * L + i) << logN) + n];
-            const u64 kd = key[((((u64)(k0 + kk) * 2 + 1) * L + i) << logN) + n];
-            mac128(a1, kd, p);
-            mac128(a2, km, p);
-            if ((kk & 7) == 7) {
-                a1.lo = red128_full(a1, pc);
-                a1.hi = 0;
-                a2.lo = red128_full(a2, pc);
-                a2.hi = 0;
+        const u64* dp = dig + (((b * Dn) * L + i) << logN) + n;
+        const u64* kp = key + ((((u64)k0 * 2) * L + i) << logN) + n;
+        u32 pending = 0, kk = 0;
+        for (; kk + U <= Dn; kk += U) {
+            if (pending + U > cap) {
+                a1.lo = red128_full(a1, pc); a1.hi = 0;
+                a2.lo = red128_full(a2, pc); a2.hi = 0;
+                pending = 0;
             }
+            u64 p[U], km[U], kd[U];
+#pragma unroll
+            for (u32 u = 0; u < U; u++) {
+                p[u] = dp[(u64)(kk + u) * kstride];
+                km[u] = kp[(u64)(kk + u) * 2 * kstride];
+                kd[u] = kp[(u64)(kk + u) * 2 * kstride + kstride];
+            }
+#pragma unroll
+            for (u32 u = 0; u < U; u++) {
+                mac128(a1, kd[u], p[u]);
+                mac128(a2, km[u], p[u]);
+            }
+            pending += U;
+        }
+        for (; kk < Dn; kk++) {
+            if (pending + 1 > cap) {
+                a1.lo = red128_full(a1, pc); a1.hi = 0;
+                a2.lo = red128_full(a2, pc); a2.hi = 0;
+                pending = 0;
+            }
+            const u64 p = dp[(u64)kk * kstride];
+            mac128(a1, kp[(u64)kk * 2 * kstride + kstride], p);
+            mac128(a2, kp[(u64)kk * 2 * kstride], p);
+            pending++;
         }
         *o1 = red128_full(a1, pc);
         *o2 = red128_full(a2, pc);
@@ -683,9 +773,20 @@ __global__ void ks_accum_kernel(const u64* __restrict__ dig, const u64* __restri
 int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
                     cudaStream_t st) {
     if (!batch) return TFB_OK;
-    const u64 total = batch * c->L * c->N;
-    const unsigned tb = 256, nb = grid_for(total, tb);
-    { ProfScope ps(PC_KS_ACCUM, st); ks_accum_kernel<<<nb, tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total); }
+    long double qm = 0;
+    for (u32 i = 0; i < c->L; i++) qm = (long double)c->q[i] > qm ? (long double)c->q[i] : qm;
+    // products of canonical residues are below qmax^2; one slot is left for the carried (reduced) value
+    long double terms = 3.402823669209384634e38L / (qm * qm);
+    const u32 cap = terms >= 1e6L ? 1000000u : (terms >= 3.0L ? (u32)terms - 1 : 1u);
+    if (c->logN < 1) { tfb_set_error("keyswitch: ring degree too small"); return TFB_EUNSUPPORTED; }
+    const u64 total2 = batch * c->L * c->N / 2;
+    const unsigned tb = 256;
+    ProfScope ps(PC_KS_ACCUM, st);
+    if (total2 < 400000) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
+        ks_accum1_kernel<<<grid_for(2 * total2, tb), tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, 2 * total2, cap);
+    } else {
+        ks_accum_kernel<<<grid_for(total2, tb), tb, 0, st>>>((const ulonglong2*)dig, (const ulonglong2*)key, (ulonglong2*)acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total2, cap);
+    }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
