@@ -39,5 +39,18 @@ D = T.ndigits(allq[:L], 2)
 key = cq.ntt_fwd(cq.to_device(rnd(rng, allq[:L], (D, 2), N)))
 ks = cq.keyswitch(key, cq.to_device(rnd(rng, allq[:L], (2, 3), N)), 2)
 rs = cq.rescale(cq.to_device(c1))
+from toyfhe_b200 import sharding as S
+lo, hi = S.shard_range(L, 1, 3)
+shard = T.Context(N, allq[lo:hi], allpsi[lo:hi])
+ct3 = cq.to_device(rnd(rng, allq[:L], (2, 3), N))
+part = cq.keyswitch_shard(shard, lo, S.key_rows_for_shard(key, lo, hi), ct3, 2)
+assert torch.equal(part, cq.keyswitch(key, ct3, 2)[:, :, lo:hi, :])
+import math
+Q = math.prod(allq[:L])
+m = rng.integers(0, t, size=(2, N), dtype=np.uint64)
+dec = cq.bfv_decode(t, Q // t, cq.bfv_encode(t, Q // t, cq.to_device(m)))
+assert np.array_equal(H(dec), m)
+u = cq.sample_uniform(1, 2, (2,))
+g = cq.sample_gaussian(3.2, 1, 3, (2,))
 torch.cuda.synchronize()
-print("keyswitch / rescale ran", flush=True)
+print("keyswitch / keyswitch_shard / rescale / encode / decode / samplers ran", flush=True)
