@@ -152,6 +152,16 @@ int tfb_bfv_mul(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1
 int tfb_bfv_encode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream);
 int tfb_bfv_decode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
 
+/* ---- CKKS encoding on the device -------------------------
+ * The complex-FFT maps of src/ckksencoding.jl between N/2 complex slots (interleaved re, im float64, device memory)
+ * and a real-coefficient plaintext polynomial; `scale` is the FixedRational denominator (ckks.jl:30-47).
+ * encode (ckksencoding.jl:76-101): slots [polys][N/2] -> out [polys][L][N] primal, round(scale * coefficient) embedded
+ *        in every prime; |scale * coefficient| must stay below 2^62.
+ * decode (ckksencoding.jl:60-70):  in [polys][L][N] primal -> slots [polys][N/2] (centred lift / scale, DFT).
+ * Floating point like the reference's FFTW calls: parity is the reference tests' tolerance, not bit-exactness. */
+int tfb_ckks_encode(tfb_ctx* ctx, double scale, const double* slots, uint64_t* out, uint64_t polys, void* stream);
+int tfb_ckks_decode(tfb_ctx* ctx, double scale, const uint64_t* in, double* slots, uint64_t polys, void* stream);
+
 /* ---- sampling on the device ------------------------------
  * RingSampler (poly.jl:7-23) for keygen / encrypt (rlwe_she.jl:155-195).  The reference's RNG is Julia's unseeded
  * global one, so parity with it is statistical only; these are counter-based (Philox4x32-10, key = seed, counter =

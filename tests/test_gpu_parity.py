@@ -247,6 +247,65 @@ def test_bfv_mul_joint_basis_extreme_residues():
     assert np.array_equal(got, want)
 
 
+# --------------------------------------------------------------------- CKKS encoding on the device (ckksencoding.jl:60-101)
+def _ckks_encode_host(data, scale, N):
+    """ckksencoding.jl:76-101 with numpy's FFT and exact rational rounding (the host route of scheme.CKKSEncoding)"""
+    from fractions import Fraction
+    n = N // 2
+    cm = np.zeros(N, dtype=np.complex128)
+    g = 1
+    for i in range(n):
+        g = g * 3 % (2 * N)
+        cm[g >> 1] = data[i]
+        cm[(2 * N - g) >> 1] = np.conj(data[i])
+    nip = np.fft.ifft(cm) * np.exp(2j * np.pi * np.arange(N) / (2 * N))
+    assert np.abs(nip.imag).max() < 1e-9 * max(1.0, np.abs(nip).max())
+    return [int(round(Fraction(float(x)) * Fraction(scale))) for x in nip.real]
+
+
+@pytest.mark.parametrize("logN,logqs,scale", [(5, [40, 40, 40], 2.0 ** 40), (13, [60, 40, 40], 2.0 ** 40), (15, [60, 40], 2.0 ** 30), (4, [40, 40], 2.0 ** 60 / 3)])
+def test_ckks_encode_decode(logN, logqs, scale):
+    """tfb_ckks_encode / tfb_ckks_decode against the numpy restatement of ckksencoding.jl: encoded integers equal up
+    to one unit where float64 rounding decides a half-integer, decode(encode(z)) = z and decode of arbitrary centred
+    coefficients equal to the host formula within the reference tests' tolerances; batches of polynomials"""
+    import torch
+    N = 1 << logN
+    qs, psis, ctx, _ = _ring(N, logqs)
+    Q = math.prod(qs)
+    rng = np.random.default_rng(logN)
+    P = 3
+    z = rng.uniform(-4, 4, (P, N // 2)) + 1j * rng.uniform(-4, 4, (P, N // 2))
+    z[0, :2] = [1.0, -2.5j]
+    d = torch.from_numpy(z).cuda()
+    enc = H(ctx.ckks_encode(scale, d))
+    mag = scale * 8
+    for p in range(P):
+        want = _ckks_encode_host(z[p], scale, N)
+        tol = max(1.0, mag * 2e-15 * logN)                                                       # float64 FFT round-off, then one rounding
+        d0 = None
+        for i, q in enumerate(qs):                                                               # the same integer under every prime
+            di = [((int(a) - w) % q + q // 2) % q - q // 2 for a, w in zip(enc[p, i], want)]      # centred difference mod q_i
+            assert max(abs(v) for v in di) <= tol
+            assert d0 is None or di == d0
+            d0 = di
+    back = ctx.ckks_decode(scale, ctx.ckks_encode(scale, d)).cpu().numpy()
+    assert np.allclose(back, z, atol=max(1e-9, 4 * N / scale))
+    # decode of arbitrary coefficients (large centred values): host formula of ckksencoding.jl:60-70
+    xs = [int.from_bytes(rng.bytes(32), "little") % Q for _ in range(N)]
+    xs[:4] = [0, 1, Q - 1, Q // 2]
+    res = np.array([[x % q for x in xs] for q in qs], dtype=np.uint64)[None]
+    cen = np.array([float(x - Q if x > Q // 2 else x) / scale for x in xs])
+    F = np.fft.fft(cen * np.exp(-2j * np.pi * np.arange(N) / (2 * N)))
+    g, idx = 1, []
+    for _ in range(N // 2):
+        g = g * 3 % (2 * N)
+        idx.append(g >> 1)
+    got = ctx.ckks_decode(scale, ctx.to_device(res)).cpu().numpy()[0]
+    assert np.allclose(got, F[idx], rtol=1e-9, atol=1e-9 * np.abs(F).max())
+    with pytest.raises(T.EngineError):
+        ctx.ckks_encode(2.0 ** 70, d)                                                            # scale * coefficient beyond 63 bits
+
+
 # --------------------------------------------------------------------- sampling on the device (poly.jl:7-23)
 def test_device_sampler_matches_its_cpu_restatement_and_the_distributions():
     """tfb_sample_uniform / tfb_sample_gaussian vs oracle/sampler_oracle.py (same Philox counters): uniform residues

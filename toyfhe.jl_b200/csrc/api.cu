@@ -231,6 +231,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->d_ginv = nullptr;
     c->d_halfmr = nullptr;
     c->ws = c->stage = c->io = nullptr;
+    c->d_ckks_pos = nullptr;
     c->ws_bytes = c->stage_bytes = c->io_bytes = 0;
     c->conv_ok = false;
     c->num_sms = 0;
@@ -304,6 +305,7 @@ int tfb_ctx_destroy(tfb_ctx* c) {
     cudaFree(c->ws);
     cudaFree(c->stage);
     cudaFree(c->io);
+    cudaFree(c->d_ckks_pos);
     delete c;
     return TFB_OK;
 }
@@ -469,6 +471,18 @@ int tfb_bfv_decode(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, c
     return launch_bfv_decode(c, t, delta, nl, b, out, polys, (cudaStream_t)stream);
 }
 
+int tfb_ckks_encode(tfb_ctx* c, double scale, const double* slots, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(slots); CHECK_PTR(out);
+    return launch_ckks_encode(c, scale, slots, out, polys, (cudaStream_t)stream);
+}
+int tfb_ckks_decode(tfb_ctx* c, double scale, const uint64_t* in, double* slots, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(slots);
+    return launch_ckks_decode(c, scale, in, slots, polys, (cudaStream_t)stream);
+}
 int tfb_sample_uniform(tfb_ctx* c, uint64_t seed, uint32_t stream_id, uint64_t* out, uint64_t polys, void* stream) {
     CHECK_CTX(c);
     if (!polys) return TFB_OK;

@@ -39,6 +39,7 @@ struct tfb_ctx {
     size_t stage_bytes;
     void* io;
     size_t io_bytes;
+    unsigned* d_ckks_pos;   // [N/2] slot positions (3^(i+1) mod 2N) >> 1 of the CKKS encoding (ckks_kernels.cu), built on first use
 };
 
 void tfb_set_error(const std::string& msg);
@@ -91,6 +92,9 @@ int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, 
 int launch_bfv_encode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* m, u64* out, u64 polys, cudaStream_t st);
 int launch_bfv_decode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int build_garner(tfb_ctx* c);
+// ckks_kernels.cu
+int launch_ckks_encode(tfb_ctx* c, double scale, const double* slots, u64* out, u64 polys, cudaStream_t st);
+int launch_ckks_decode(tfb_ctx* c, double scale, const u64* in, double* slots, u64 polys, cudaStream_t st);
 // sample_kernels.cu
 int launch_sample_uniform(tfb_ctx* c, u64 seed, u32 stream, u64* out, u64 polys, cudaStream_t st);
 int launch_sample_gaussian(tfb_ctx* c, double sigma, u64 seed, u32 stream, u64* out, u64 polys, cudaStream_t st);

@@ -993,3 +993,43 @@ int launch_bfv_decode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* in
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
+
+// ---------------------------------------- CKKS decode front end (ckksencoding.jl:60-66, ckks.jl:52-58)
+// v[p][k] = (centred lift of coefficient k) / scale * exp(-i pi k / N) as a complex double.  The lift is evaluated
+// from the mixed-radix digits by Horner in float64 (|x| = sum d_i prod_{j<i} q_j): relative error ~ L 2^-53, the
+// precision of the reference's own Float64(n / denom).
+struct LiftQ { double q[MAXD]; };
+__global__ void ckks_lift_kernel(const u64* __restrict__ in, double* __restrict__ v, const u32 L, const u32 logN, const double scale,
+                                 const GarnerTab g, const PrimeParams* __restrict__ pp, const LiftQ lq, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 k = (u32)(idx & (N - 1));
+    u64 r[MAXD], d[MAXD];
+    for (u32 i = 0; i < L; i++) r[i] = in[((p * L + i) << logN) + k];
+    garner_digits(r, d, L, g, pp);
+    const bool neg = mr_above_half(d, L, g.halfmr);
+    if (neg) {   // |x| = Q - X: digits of the negated residues
+        for (u32 i = 0; i < L; i++) r[i] = neg_mod(r[i], pp[i].pc.q);
+        garner_digits(r, d, L, g, pp);
+    }
+    double x = 0.0;
+    for (int i = (int)L - 1; i >= 0; i--) x = x * lq.q[i] + (double)d[i];
+    x = (neg ? -x : x) / scale;
+    double s, c;
+    sincospi(-(double)k / (double)N, &s, &c);
+    v[2 * idx] = x * c;
+    v[2 * idx + 1] = x * s;
+}
+int launch_ckks_lift(tfb_ctx* c, double scale, const u64* in, double* v, u64 polys, cudaStream_t st) {
+    if (c->L > MAXD || !c->conv_ok) { tfb_set_error("ckks decode: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    LiftQ lq;
+    for (u32 i = 0; i < c->L; i++) lq.q[i] = (double)c->q[i];
+    const u64 total = polys * c->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_LEVEL, st); ckks_lift_kernel<<<(unsigned)nb, tb, 0, st>>>(in, v, c->L, c->logN, scale, garner_of(c), c->d_pp, lq, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}

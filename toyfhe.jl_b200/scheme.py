@@ -541,7 +541,11 @@ class CKKSEncoding:
 
     @classmethod
     def from_ring_element(cls, plain: RingElement, scale: float) -> "CKKSEncoding":
-        """decode (ckksencoding.jl:60-70)"""
+        """decode (ckksencoding.jl:60-70): on the device (tfb_ckks_decode) when the ring fits the engine's exact
+        conversions; the numpy route below is kept for rings beyond that"""
+        ctx = plain.ring.ctx
+        if plain.ring.L <= 32 and plain.ring.N >= 4:
+            return cls(scale, ctx.ckks_decode(scale, plain.coeffs_primal()).cpu().numpy().reshape(-1))
         N = plain.ring.N
         scaled = np.array([x / scale for x in plain.to_signed_ints()], dtype=np.float64)   # FixedRational -> Float64 (ckks.jl:52-58)
         k = np.arange(N)
@@ -551,10 +555,15 @@ class CKKSEncoding:
         return cls(scale, F[idx])
 
     def to_ring_element(self, ring: NegacyclicRing) -> RingElement:
-        """encode (ckksencoding.jl:76-101)"""
+        """encode (ckksencoding.jl:76-101): on the device (tfb_ckks_encode) when scale * coefficient fits 62 bits;
+        otherwise (e.g. the 2^70 scales of docs/src/man/ckks.md) the exact big-integer route below"""
         n = len(self.data)
         N = 2 * n
         assert ring.N == N
+        if N >= 4 and self.scale * max(1.0, float(np.abs(self.data).max())) < 2.0 ** 61:
+            import torch
+            d = torch.from_numpy(np.ascontiguousarray(self.data)).to(f"cuda:{ring.ctx.device}")
+            return RingElement(ring, primal=ring.ctx.ckks_encode(self.scale, d.reshape(1, n))[0])
         cm = np.zeros(N, dtype=np.complex128)
         for i in range(n):
             cm[_zmstar(2 * N, 1, i + 1) >> 1] = self.data[i]
