@@ -173,6 +173,33 @@ TFB_HD void pass3_compute_store(u64* x, u64* __restrict__ orow, const tw_t* __re
     typedef NttGeo<R> Geo;
     const u32 w = t >> 5, lane = t & 31;
     const u32 oblk = S0ZERO ? 0 : brev_bits(blk, (int)s0);
+#ifdef __CUDA_ARCH__
+    // The G groups run the SAME code on different registers.  With 8 groups (N = 2^12) the loop is kept rolled -- the
+    // group's residues are rotated into x[0..RS) -- which shrinks the instruction footprint (+2.5 % there); with 2 or 4
+    // groups the unrolled form is faster (measured: -2 % / -3.5 % rolled at N = 2^14 / 2^13, profiles/r01_ntt_sizes.txt).
+    constexpr bool ROLL = Geo::G >= 8;
+#else
+    constexpr bool ROLL = false;
+#endif
+    if (ROLL) {
+#pragma unroll 1
+    for (int g = 0; g < (int)Geo::G; g++) {
+        const u32 k2 = Geo::G * w + g;
+        u32 tb[R];
+#pragma unroll
+        for (int u = 1; u <= R; u++) tb[u - 1] = pass3_base<R>(blk, (u32)g, u, t);
+        levels3<R, Lay<R>::P3MASK>(x, twc, tb, rp, Geo::T);
+#pragma unroll
+        for (int c = 0; c < (int)Geo::RS; c++) {
+            const u32 kl = (brev_bits((u32)c, R) << 10) | (k2 << 5) | lane;
+            if (S0ZERO) orow[kl] = canon3(x[c], rp);
+            else orow[((u64)kl << s0) + oblk] = canon3(x[c], rp);
+        }
+        // rotate the remaining groups down by one
+#pragma unroll
+        for (int c = 0; c < (int)(Geo::G - 1) * (int)Geo::RS; c++) x[c] = x[c + Geo::RS];
+    }
+    } else {
 #pragma unroll
     for (int g = 0; g < (int)Geo::G; g++) {
         const u32 k2 = Geo::G * w + g;
@@ -186,6 +213,7 @@ TFB_HD void pass3_compute_store(u64* x, u64* __restrict__ orow, const tw_t* __re
             if (S0ZERO) orow[kl] = canon3(x[g * Geo::RS + c], rp);
             else orow[((u64)kl << s0) + oblk] = canon3(x[g * Geo::RS + c], rp);
         }
+    }
     }
 }
 
