@@ -611,7 +611,11 @@ __global__ void ks_digits_pow2_kernel(const u64* __restrict__ cend, const u64 ct
         X[nl++] = carry;
     }
     const u64 mask = w >= 64 ? ~0ull : ((1ull << w) - 1);
-    for (u32 kk = 0; kk < Dn; kk++) {
+    // blockIdx.y splits the digit range: small batches have too few coefficients to fill the GPU, so several CTAs
+    // repeat the (cheap) reconstruction of a coefficient and each writes its own slice of the digits
+    const u32 per = (Dn + gridDim.y - 1) / gridDim.y;
+    const u32 kbeg = blockIdx.y * per, kend = kbeg + per < Dn ? kbeg + per : Dn;
+    for (u32 kk = kbeg; kk < kend; kk++) {
         const u32 bit = (k0 + kk) * w, limb = bit >> 6, off = bit & 63;
         u64 v = limb < nl ? X[limb] >> off : 0;
         if (off + w > 64 && limb + 1 < nl) v |= X[limb + 1] << (64 - off);
@@ -638,7 +642,10 @@ int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct
         const u64 total = batch * c->N;
         const unsigned tb = 128;
         const u64 nb = (total + tb - 1) / tb;
-        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_pow2_kernel<<<(unsigned)nb, tb, 0, st>>>(cend, ct_stride, out, c->L, target->L, c->logN, (u32)w, k0, Dn,
+        u64 chunks = nb < 2368 ? 2368 / nb : 1;             // aim at 16 CTAs per SM
+        if (chunks > (Dn + 7) / 8) chunks = (Dn + 7) / 8;   // at least 8 digits per slice
+        if (chunks < 1) chunks = 1;
+        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_pow2_kernel<<<dim3((unsigned)nb, (unsigned)chunks), tb, 0, st>>>(cend, ct_stride, out, c->L, target->L, c->logN, (u32)w, k0, Dn,
                                                           garner_of(c), c->d_pp, target->d_pp, total); }
     }
     TFB_CUDA(cudaGetLastError());
