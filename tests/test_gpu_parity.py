@@ -398,7 +398,9 @@ def test_keyswitch_digits(w):
 
 
 @pytest.mark.parametrize("N,logqs,w,comps", [(64, [60, 60, 40], 0, 3), (64, [60, 60, 40], 7, 3), (64, [50, 50], 1, 2),
-                                             (2048, [50, 50], 1, 3), (1024, [60] * 4, 2, 3)])
+                                             (2048, [50, 50], 1, 3), (1024, [60] * 4, 2, 3),
+                                             # N = 2^12, 2^13: base-2^w digits written once and transformed under every prime
+                                             (4096, [60, 60, 40], 2, 3), (4096, [50, 50], 7, 2), (8192, [60, 40, 40], 3, 3)])
 def test_keyswitch_plain(N, logqs, w, comps):
     qs, psis, ctx, orc = _ring(N, logqs)
     rng = np.random.default_rng(N + w)

@@ -606,6 +606,26 @@ int tfb_keyswitch_digits(tfb_ctx* c, tfb_ctx* target, uint32_t w, const uint64_t
     return launch_ks_digits(c, target, (int)w, cend, (u64)c->L * c->N, out, 0, D, batch, (cudaStream_t)stream);
 }
 
+// digit polynomials k0 .. k0+dn-1 of cend, in the NTT domain of ring r: dig [batch][dn][r->L][N].  Base-2^w digits are
+// small integers (below every prime when 2^w <= min q): they are written ONCE as [batch][dn][N] and the forward kernel
+// reads each row under all r->L primes (launch_ntt_bcast) instead of materialising r->L identical copies first.
+static int ks_digits_dual(tfb_ctx* c, tfb_ctx* r, uint32_t w, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch,
+                          cudaStream_t st) {
+    int rc;
+    bool small = w > 0 && w < 62;
+    for (u32 i = 0; small && i < r->L; i++) small = (1ull << w) <= r->q[i];
+    if (small && r->L > 1 && r->v3_ok && r->logN >= 12 && r->logN <= 14) {
+        const size_t need = (size_t)batch * dn * r->N * sizeof(u64);
+        if ((rc = ws_reserve(r, need))) return rc;
+        u64* compact = (u64*)r->ws;
+        if ((rc = launch_ks_digits(c, r, (int)w, cend, ct_stride, compact, k0, dn, batch, st, true))) return rc;
+        rc = launch_ntt_bcast(r, compact, dig, (u64)batch * dn, st);
+        if (rc != -1) return rc;
+    }
+    if ((rc = launch_ks_digits(c, r, (int)w, cend, ct_stride, dig, k0, dn, batch, st))) return rc;
+    return launch_ntt(r, dig, dig, (u64)batch * dn * r->L, false, st);
+}
+
 int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
                   uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(c);
@@ -637,8 +657,7 @@ int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual
     const u64* cend = ct + (size_t)(comps - 1) * polyc;
     for (u32 k0 = 0; k0 < Dneed; k0 += dch) {
         const u32 dn = Dneed - k0 < dch ? Dneed - k0 : dch;
-        if ((rc = launch_ks_digits(c, r, (int)w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;
-        if ((rc = launch_ntt(r, dig, dig, (u64)batch * dn * r->L, false, st))) return rc;
+        if ((rc = ks_digits_dual(c, r, w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;
         if ((rc = launch_ks_accum(r, k0, dn, dig, key_dual, acc, k0 ? 1 : 0, batch, st))) return rc;
     }
     if ((rc = launch_ntt(r, acc, acc, 2 * batch * r->L, true, st))) return rc;
@@ -673,8 +692,7 @@ int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, cons
     const u64* cend = ct + (size_t)(comps - 1) * polyc;
     for (u32 k0 = 0; k0 < Dneed; k0 += dch) {
         const u32 dn = Dneed - k0 < dch ? Dneed - k0 : dch;
-        if ((rc = launch_ks_digits(c, r, (int)w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;   // digits of the WHOLE integer, embedded in the shard's primes
-        if ((rc = launch_ntt(r, dig, dig, (u64)batch * dn * r->L, false, st))) return rc;
+        if ((rc = ks_digits_dual(c, r, w, cend, (u64)comps * polyc, dig, k0, dn, batch, st))) return rc;   // digits of the WHOLE integer under the shard's primes
         if ((rc = launch_ks_accum(r, k0, dn, dig, key_dual, acc, k0 ? 1 : 0, batch, st))) return rc;
     }
     if ((rc = launch_ntt(r, acc, acc, 2 * batch * r->L, true, st))) return rc;

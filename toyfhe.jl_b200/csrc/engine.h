@@ -83,7 +83,7 @@ int launch_crt_expand(tfb_ctx* c, u64 P, const u64* in, u64* out, u64 polys, cud
 int launch_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int launch_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct_stride, u64* out, u32 k0, u32 Dn,
-                     u64 batch, cudaStream_t st);
+                     u64 batch, cudaStream_t st, bool compact = false);
 int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
                     cudaStream_t st);
 int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* out, u64 batch, cudaStream_t st, u32 Lct = 0, u32 first = 0);
@@ -116,6 +116,8 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
 // ntt_kernels4.cu
 int ntt4_setup_device();
 int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
+int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
 // ntt_kernels5.cu
 int ntt5_setup_device();
 int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);

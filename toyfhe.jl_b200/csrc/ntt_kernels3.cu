@@ -241,8 +241,8 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
     } else {
         ProfScope ps(PC_NTT_FWD, st);
         if (c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2) {
-            if (s0 == 0) v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units);
-            else v3k::ntt_fwd_s_kernel<4, false><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
+            if (s0 == 0) v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units, 1);
+            else v3k::ntt_fwd_s_kernel<4, false><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units, 1);
         }
         else if (c->ntt_mode >= 1 && !g_ntt_force_harvey && g_ntt_max_mode >= 1)
             ntt_fwd14p_kernel<1><<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
@@ -251,4 +251,21 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
     }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
+}
+
+// forward NTT of `polys` small-integer polynomials (in [polys][N], values below every prime) under all L primes:
+// out [polys][L][N].  Returns -1 when the third-generation kernel does not apply (the caller replicates the rows).
+int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!c->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || g_ntt_version != 3) return -1;
+    const u64 rows = polys * c->L;
+    if (c->logN == 14) {
+        if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+        const int nsm = c->num_sms > 0 ? c->num_sms : 148;
+        const unsigned grid = (unsigned)(rows < (u64)nsm ? rows : (u64)nsm);
+        ProfScope ps(PC_NTT_FWD, st);
+        v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, c->L);
+        TFB_CUDA(cudaGetLastError());
+        return TFB_OK;
+    }
+    return launch_ntt_s_bcast(c, in, out, polys, st);
 }

@@ -17,3 +17,9 @@ int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cu
     if (c->logN == 13) return v3k::launch_s<3>(c, in, out, rows, inverse, st);
     return -1;
 }
+
+int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (c->logN == 12) return v3k::launch_s<2>(c, in, out, polys * c->L, false, st, c->L);
+    if (c->logN == 13) return v3k::launch_s<3>(c, in, out, polys * c->L, false, st, c->L);
+    return -1;
+}

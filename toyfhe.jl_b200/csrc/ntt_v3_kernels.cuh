@@ -60,7 +60,7 @@ __device__ __forceinline__ void build_redtab(v3::redent_t* redtab, const PrimePa
 template <int R, bool S0ZERO>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
-                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits) {
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits, const u32 in_div) {
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
@@ -75,8 +75,10 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     }
     build_redtab(redtab, pp, L, t, Geo::T);
     __syncthreads();
+    // in_div > 1 (s0 = 0 only): input row = unit / in_div -- one small-integer polynomial (a keyswitch digit) is
+    // transformed under in_div consecutive primes without being replicated in memory first
     if (t < 32 && unit < nunits)
-        tma_load_row_skewed<R>(smem, in + (u64)(unit >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N, &bar, t);
+        tma_load_row_skewed<R>(smem, in + (u64)((unit / in_div) >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N, &bar, t);
     u32 parity = 0;
     u64 x[32];
     for (; unit < nunits; unit += gridDim.x) {
@@ -98,7 +100,7 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         __syncthreads();
         const u32 next = unit + gridDim.x;
         if (t < 32 && next < nunits)
-            tma_load_row_skewed<R>(smem, in + (u64)(next >> s0) * nrow + (u64)(next & ((1u << s0) - 1)) * Geo::N, &bar, t);
+            tma_load_row_skewed<R>(smem, in + (u64)((next / in_div) >> s0) * nrow + (u64)(next & ((1u << s0) - 1)) * Geo::N, &bar, t);
         v3::pass3_compute_store<R, S0ZERO>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
     }
 }
@@ -204,7 +206,7 @@ int setup_s() {
 }
 // rows of exactly N = 2^(10+R) positions
 template <int R>
-int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st) {
+int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st, u32 in_div = 1) {
     typedef NttGeo<R> Geo;
     if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
     const u64 slots = (u64)(c->num_sms > 0 ? c->num_sms : 148) * (512 / Geo::T);
@@ -214,7 +216,7 @@ int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaSt
         ntt_inv_s_kernel<R><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)rows);
     } else {
         ProfScope ps(PC_NTT_FWD, st);
-        ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows);
+        ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, in_div);
     }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;

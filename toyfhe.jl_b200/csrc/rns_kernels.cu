@@ -620,6 +620,10 @@ __global__ void ks_digits_pow2_kernel(const u64* __restrict__ cend, const u64 ct
         u64 v = limb < nl ? X[limb] >> off : 0;
         if (off + w > 64 && limb + 1 < nl) v |= X[limb + 1] << (64 - off);
         v &= mask;
+        if (Lt == 0) {   // compact: one row per digit (the digit is below every prime; launch_ntt_bcast transforms it under all of them)
+            out[((b * Dn + kk) << logN) + n] = v;
+            continue;
+        }
         for (u32 j = 0; j < Lt; j++) {
             const PrimeConst pc = ppt[j].pc;
             out[(((b * Dn + kk) * Lt + j) << logN) + n] = v < pc.q ? v : barrett_red64(v, pc);
@@ -628,10 +632,11 @@ __global__ void ks_digits_pow2_kernel(const u64* __restrict__ cend, const u64 ct
 }
 
 int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct_stride, u64* out, u32 k0, u32 Dn,
-                     u64 batch, cudaStream_t st) {
+                     u64 batch, cudaStream_t st, bool compact) {
     if (!batch || !Dn) return TFB_OK;
     if (c->N != target->N) { tfb_set_error("keyswitch digits: ring degrees differ"); return TFB_EINVAL; }
     if (w < 0 || w > 63) { tfb_set_error("keyswitch digits: relin_window must be in 0..63"); return TFB_EINVAL; }
+    if (compact && w == 0) { tfb_set_error("internal: CRT digits have no compact form"); return TFB_EINVAL; }
     if (w == 0) {
         if (k0 + Dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
         const u64 total = batch * Dn * c->N;
@@ -645,7 +650,7 @@ int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct
         u64 chunks = nb < 2368 ? 2368 / nb : 1;             // aim at 16 CTAs per SM
         if (chunks > (Dn + 7) / 8) chunks = (Dn + 7) / 8;   // at least 8 digits per slice
         if (chunks < 1) chunks = 1;
-        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_pow2_kernel<<<dim3((unsigned)nb, (unsigned)chunks), tb, 0, st>>>(cend, ct_stride, out, c->L, target->L, c->logN, (u32)w, k0, Dn,
+        { ProfScope ps(PC_KS_DIGITS, st); ks_digits_pow2_kernel<<<dim3((unsigned)nb, (unsigned)chunks), tb, 0, st>>>(cend, ct_stride, out, c->L, compact ? 0 : target->L, c->logN, (u32)w, k0, Dn,
                                                           garner_of(c), c->d_pp, target->d_pp, total); }
     }
     TFB_CUDA(cudaGetLastError());
