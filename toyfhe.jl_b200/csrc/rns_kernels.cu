@@ -671,11 +671,14 @@ __global__ void ks_accum_kernel(const ulonglong2* __restrict__ dig, const ulongl
     constexpr u32 U = 4;
     const u32 lg2 = logN - 1;                    // rows in units of two coefficients (128-bit accesses)
     const u64 kstride = (u64)L << lg2;           // between consecutive digit rows of one (b, i) and between key components
-    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
-        const u64 n2 = idx & ((1ull << lg2) - 1);
-        const u64 r = idx >> lg2;  // (b, i)
-        const u64 b = r / L;
-        const u32 i = (u32)(r % L);
+    // CTAs that run together work on the SAME key rows for different ciphertexts (b varies fastest over the tiles), so
+    // the key -- larger than L2 at base 4 -- comes from HBM once per batch instead of once per ciphertext
+    const u64 tiles = total2 / blockDim.x;                 // launch_ks_accum guarantees blockDim.x | N/2
+    const u64 B = total2 / ((u64)L << lg2), cpr = (1ull << lg2) / blockDim.x;
+    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const u64 b = tile % B, rest = tile / B;
+        const u64 n2 = (rest % cpr) * blockDim.x + threadIdx.x;
+        const u32 i = (u32)(rest / cpr);
         const PrimeConst pc = pp[i].pc;
         acc128 a1x = {0, 0}, a1y = {0, 0}, a2x = {0, 0}, a2y = {0, 0};
         ulonglong2* o1 = acc + (((b * 2 + 0) * L + i) << lg2) + n2;
@@ -794,7 +797,7 @@ int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, 
     const u64 total2 = batch * c->L * c->N / 2;
     const unsigned tb = 256;
     ProfScope ps(PC_KS_ACCUM, st);
-    if (total2 < 400000) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
+    if (total2 < 200000 || (c->N / 2) % tb != 0) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
         ks_accum1_kernel<<<grid_for(2 * total2, tb), tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, 2 * total2, cap);
     } else {
         ks_accum_kernel<<<grid_for(total2, tb), tb, 0, st>>>((const ulonglong2*)dig, (const ulonglong2*)key, (ulonglong2*)acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total2, cap);
