@@ -68,11 +68,12 @@ ntt_inv_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
 }
 
 // ------------------------------------------------- global stages (N > 2^14)
-// forward level s (1-based) over whole rows, canonical in -> canonical out
+// forward level s (1-based) over whole rows, canonical in -> canonical out.  Each thread handles TWO adjacent
+// butterflies of one block (half >= 2^14 here), so every access is 128 bits wide.
 __global__ void ntt_fwd_stage_kernel(const u64* __restrict__ in, u64* __restrict__ out,
                                      const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ pp,
                                      const u32 L, const u32 logN, const u32 s, const u64 total) {
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 gid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (gid >= total) return;
     const u64 row = gid >> (logN - 1);
     const u32 i = (u32)(gid & ((1ull << (logN - 1)) - 1));
@@ -82,15 +83,16 @@ __global__ void ntt_fwd_stage_kernel(const u64* __restrict__ in, u64* __restrict
     const u32 j = i >> (logN - s), k = i & (half - 1);
     const u64 p0 = (row << logN) + ((u64)j << (logN - s + 1)) + k;
     const tw_t w = tw_all[((u64)prime << logN) + (1u << (s - 1)) + j];
-    const u64 X = in[p0], T = shoup_full(in[p0 + half], w.w, w.wp, q);
-    out[p0] = add_mod(X, T, q);
-    out[p0 + half] = sub_mod(X, T, q);
+    const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(in + p0), Y = *reinterpret_cast<const ulonglong2*>(in + p0 + half);
+    const u64 T0 = shoup_full(Y.x, w.w, w.wp, q), T1 = shoup_full(Y.y, w.w, w.wp, q);
+    *reinterpret_cast<ulonglong2*>(out + p0) = make_ulonglong2(add_mod(X.x, T0, q), add_mod(X.y, T1, q));
+    *reinterpret_cast<ulonglong2*>(out + p0 + half) = make_ulonglong2(sub_mod(X.x, T0, q), sub_mod(X.y, T1, q));
 }
 // inverse level s; level 1 folds in N^-1
 __global__ void ntt_inv_stage_kernel(const u64* __restrict__ in, u64* __restrict__ out,
                                      const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ pp,
                                      const u32 L, const u32 logN, const u32 s, const u64 total) {
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 gid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (gid >= total) return;
     const u64 row = gid >> (logN - 1);
     const u32 i = (u32)(gid & ((1ull << (logN - 1)) - 1));
@@ -101,16 +103,19 @@ __global__ void ntt_inv_stage_kernel(const u64* __restrict__ in, u64* __restrict
     const u32 j = i >> (logN - s), k = i & (half - 1);
     const u64 p0 = (row << logN) + ((u64)j << (logN - s + 1)) + k;
     const tw_t w = tw_all[((u64)prime << logN) + (1u << (s - 1)) + j];
-    const u64 X = in[p0], Y = in[p0 + half];
-    u64 S = add_mod(X, Y, q), D = sub_mod(X, Y, q);
+    const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(in + p0), Y = *reinterpret_cast<const ulonglong2*>(in + p0 + half);
+    u64 S0 = add_mod(X.x, Y.x, q), S1 = add_mod(X.y, Y.y, q), D0 = sub_mod(X.x, Y.x, q), D1 = sub_mod(X.y, Y.y, q);
     if (s == 1) {
-        S = shoup_full(S, P.ninv.w, P.ninv.wp, q);
-        D = shoup_full(D, P.ninv_w1.w, P.ninv_w1.wp, q);
+        S0 = shoup_full(S0, P.ninv.w, P.ninv.wp, q);
+        S1 = shoup_full(S1, P.ninv.w, P.ninv.wp, q);
+        D0 = shoup_full(D0, P.ninv_w1.w, P.ninv_w1.wp, q);
+        D1 = shoup_full(D1, P.ninv_w1.w, P.ninv_w1.wp, q);
     } else {
-        D = shoup_full(D, w.w, w.wp, q);
+        D0 = shoup_full(D0, w.w, w.wp, q);
+        D1 = shoup_full(D1, w.w, w.wp, q);
     }
-    out[p0] = S;
-    out[p0 + half] = D;
+    *reinterpret_cast<ulonglong2*>(out + p0) = make_ulonglong2(S0, S1);
+    *reinterpret_cast<ulonglong2*>(out + p0 + half) = make_ulonglong2(D0, D1);
 }
 
 // ------------------------------------------------------ small rows (N < 2^10)
@@ -232,7 +237,7 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     u64* tmp = (u64*)c->ws;
     const u64 total = rows << (logN - 1);
     const unsigned tb = 256;
-    const unsigned nb = (unsigned)((total + tb - 1) / tb);
+    const unsigned nb = (unsigned)((total / 2 + tb - 1) / tb);   // two butterflies per thread
     const bool pair = g_ntt_pair && g_ntt_version == 3 && c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2;
     if (!inverse) {
         // cluster-pair kernel (ntt_kernels5.cu): levels 1..s0-1 as global passes, level s0 inside the pair
