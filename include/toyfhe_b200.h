@@ -156,7 +156,8 @@ int tfb_bfv_decode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32
  * The complex-FFT maps of src/ckksencoding.jl between N/2 complex slots (interleaved re, im float64, device memory)
  * and a real-coefficient plaintext polynomial; `scale` is the FixedRational denominator (ckks.jl:30-47).
  * encode (ckksencoding.jl:76-101): slots [polys][N/2] -> out [polys][L][N] primal, round(scale * coefficient) embedded
- *        in every prime; |scale * coefficient| must stay below 2^62.
+ *        in every prime; |scale * coefficient| must stay below 2^126 (the 2^70 scales of docs/src/man/ckks.md fit);
+ *        synchronises `stream` before returning (the range check is read back).
  * decode (ckksencoding.jl:60-70):  in [polys][L][N] primal -> slots [polys][N/2] (centred lift / scale, DFT).
  * Floating point like the reference's FFTW calls: parity is the reference tests' tolerance, not bit-exactness. */
 int tfb_ckks_encode(tfb_ctx* ctx, double scale, const double* slots, uint64_t* out, uint64_t polys, void* stream);

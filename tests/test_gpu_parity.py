@@ -263,7 +263,8 @@ def _ckks_encode_host(data, scale, N):
     return [int(round(Fraction(float(x)) * Fraction(scale))) for x in nip.real]
 
 
-@pytest.mark.parametrize("logN,logqs,scale", [(5, [40, 40, 40], 2.0 ** 40), (13, [60, 40, 40], 2.0 ** 40), (15, [60, 40], 2.0 ** 30), (4, [40, 40], 2.0 ** 60 / 3)])
+@pytest.mark.parametrize("logN,logqs,scale", [(5, [40, 40, 40], 2.0 ** 40), (13, [60, 40, 40], 2.0 ** 40), (15, [60, 40], 2.0 ** 30), (4, [40, 40], 2.0 ** 60 / 3),
+                                              (6, [60, 60, 60], 2.0 ** 70)])   # docs/src/man/ckks.md scale: integers beyond 64 bits
 def test_ckks_encode_decode(logN, logqs, scale):
     """tfb_ckks_encode / tfb_ckks_decode against the numpy restatement of ckksencoding.jl: encoded integers equal up
     to one unit where float64 rounding decides a half-integer, decode(encode(z)) = z and decode of arbitrary centred
@@ -303,7 +304,7 @@ def test_ckks_encode_decode(logN, logqs, scale):
     got = ctx.ckks_decode(scale, ctx.to_device(res)).cpu().numpy()[0]
     assert np.allclose(got, F[idx], rtol=1e-9, atol=1e-9 * np.abs(F).max())
     with pytest.raises(T.EngineError):
-        ctx.ckks_encode(2.0 ** 70, d)                                                            # scale * coefficient beyond 63 bits
+        ctx.ckks_encode(2.0 ** 140, d)                                                           # scale * coefficient beyond 2^126
 
 
 # --------------------------------------------------------------------- sampling on the device (poly.jl:7-23)

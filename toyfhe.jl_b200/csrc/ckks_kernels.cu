@@ -58,12 +58,26 @@ __global__ void ckks_round_kernel(const cplx* __restrict__ v, u64* __restrict__ 
         sincospi((double)k / (double)N, &s, &c);
         const double re = (z.re * c - z.im * s) / (double)N;
         const double scaled = re * scale;
-        if (!(fabs(scaled) < 4.0e18)) { *flag = 1; continue; }
-        const long long x = llrint(scaled);
-        for (u32 i = 0; i < L; i++) {
-            const u64 q = pp[i].pc.q;
-            const u64 m = (u64)(x < 0 ? -x : x) % q;
-            out[((p * L + i) << logN) + k] = (x < 0 && m) ? q - m : m;
+        if (!(fabs(scaled) < 0x1p126)) { *flag = 1; continue; }
+        if (fabs(scaled) < 0x1p62) {
+            const long long x = llrint(scaled);             // round half to even, like round(BigInt, .) (ckks.jl:39)
+            for (u32 i = 0; i < L; i++) {
+                const u64 q = pp[i].pc.q;
+                const u64 m = (u64)(x < 0 ? -x : x) % q;
+                out[((p * L + i) << logN) + k] = (x < 0 && m) ? q - m : m;
+            }
+        } else {
+            // a double of this size is an integer already: |scaled| = m 2^e with a 53-bit m and e >= 9, below 2^126
+            int e;
+            const double fr = frexp(fabs(scaled), &e);
+            const u64 m = (u64)ldexp(fr, 53);
+            e -= 53;
+            const u64 lo = e < 64 ? m << e : 0, hi = e < 64 ? m >> (64 - e) : m << (e - 64);
+            for (u32 i = 0; i < L; i++) {
+                const PrimeConst pc = pp[i].pc;
+                const u64 r = red128_any(hi, lo, pc);
+                out[((p * L + i) << logN) + k] = (scaled < 0 && r) ? pc.q - r : r;
+            }
         }
     }
 }
@@ -123,7 +137,7 @@ int launch_ckks_encode(tfb_ctx* c, double scale, const double* slots, u64* out, 
     int h = 0;
     TFB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     TFB_CUDA(cudaStreamSynchronize(st));
-    if (h) { tfb_set_error("ckks encode: |scale * coefficient| does not fit a 63-bit integer"); return TFB_EUNSUPPORTED; }
+    if (h) { tfb_set_error("ckks encode: |scale * coefficient| must stay below 2^126"); return TFB_EUNSUPPORTED; }
     return TFB_OK;
 }
 

@@ -112,31 +112,24 @@ class BFVParams(SHEShemeParams):
     def R_cipher(self): return self.R
     def R_plain(self): return self.t
 
-    def _on_device(self) -> bool:
-        # engine limits of tfb_bfv_encode / tfb_bfv_decode: word-size t, Q / Delta < 2^40
-        return 0 < self.t < (1 << 63) and (self.Delta << 40) >= self.R.modulus()
+    def _check_range(self):
+        # engine limits of tfb_bfv_encode / tfb_bfv_decode: word-size t, Q / Delta < 2^40 (every reference test satisfies them)
+        if not (0 < self.t < (1 << 63) and (self.Delta << 40) >= self.R.modulus()):
+            raise UsageError("BFV plaintext maps: t must fit a machine word and Q / Delta must stay below 2^40")
 
     def pi_inv(self, plaintext: Sequence[int]) -> RingElement:
         """Delta * plaintext (bfv.jl:21-24) -- on the device (tfb_bfv_encode)"""
-        if not self._on_device():
-            return self.R([self.Delta * (int(m) % self.t) for m in plaintext])
+        self._check_range()
         ctx = self.R.ctx
         m = ctx.to_device(np.array([int(v) % self.t for v in plaintext], dtype=np.uint64).reshape(1, self.R.N))
         return RingElement(self.R, primal=ctx.bfv_encode(self.t, self.Delta, m)[0])
 
     def pi(self, b: RingElement) -> List[int]:
         """mod(divround(SignedMod(x), Delta), t) (bfv.jl:26-29; rounding div_hacks.jl:120-135) -- on the device
-        (tfb_bfv_decode); the big-integer loop below is only the route for parameters outside the engine's limits"""
-        if self._on_device():
-            ctx = self.R.ctx
-            return [int(v) for v in ctx.to_host(ctx.bfv_decode(self.t, self.Delta, b.coeffs_primal()))]
-        out = []
-        for x in b.to_signed_ints():
-            qq, r = divmod(abs(x), self.Delta)
-            if 2 * r >= self.Delta:
-                qq += 1
-            out.append((qq if x >= 0 else -qq) % self.t)
-        return out
+        (tfb_bfv_decode)"""
+        self._check_range()
+        ctx = self.R.ctx
+        return [int(v) for v in ctx.to_host(ctx.bfv_decode(self.t, self.Delta, b.coeffs_primal()))]
 
     def noise(self, s): return s.gaussian(self.R, self.sigma)
     def secret(self, s): return s.gaussian(self.R, self.sigma)
@@ -541,41 +534,18 @@ class CKKSEncoding:
 
     @classmethod
     def from_ring_element(cls, plain: RingElement, scale: float) -> "CKKSEncoding":
-        """decode (ckksencoding.jl:60-70): on the device (tfb_ckks_decode) when the ring fits the engine's exact
-        conversions; the numpy route below is kept for rings beyond that"""
+        """decode (ckksencoding.jl:60-70) on the device (tfb_ckks_decode)"""
         ctx = plain.ring.ctx
-        if plain.ring.L <= 32 and plain.ring.N >= 4:
-            return cls(scale, ctx.ckks_decode(scale, plain.coeffs_primal()).cpu().numpy().reshape(-1))
-        N = plain.ring.N
-        scaled = np.array([x / scale for x in plain.to_signed_ints()], dtype=np.float64)   # FixedRational -> Float64 (ckks.jl:52-58)
-        k = np.arange(N)
-        multed = scaled * np.exp(-2j * np.pi * k / (2 * N))
-        F = np.fft.fft(multed)
-        idx = [_zmstar(2 * N, 1, col) >> 1 for col in range(1, N // 2 + 1)]
-        return cls(scale, F[idx])
+        return cls(scale, ctx.ckks_decode(scale, plain.coeffs_primal()).cpu().numpy().reshape(-1))
 
     def to_ring_element(self, ring: NegacyclicRing) -> RingElement:
-        """encode (ckksencoding.jl:76-101): on the device (tfb_ckks_encode) when scale * coefficient fits 62 bits;
-        otherwise (e.g. the 2^70 scales of docs/src/man/ckks.md) the exact big-integer route below"""
+        """encode (ckksencoding.jl:76-101) on the device (tfb_ckks_encode; |scale * coefficient| < 2^126)"""
         n = len(self.data)
         N = 2 * n
         assert ring.N == N
-        if N >= 4 and self.scale * max(1.0, float(np.abs(self.data).max())) < 2.0 ** 61:
-            import torch
-            d = torch.from_numpy(np.ascontiguousarray(self.data)).to(f"cuda:{ring.ctx.device}")
-            return RingElement(ring, primal=ring.ctx.ckks_encode(self.scale, d.reshape(1, n))[0])
-        cm = np.zeros(N, dtype=np.complex128)
-        for i in range(n):
-            cm[_zmstar(2 * N, 1, i + 1) >> 1] = self.data[i]
-            cm[_zmstar(2 * N, 2, i + 1) >> 1] = np.conj(self.data[i])
-        ipoints = np.fft.ifft(cm)
-        k = np.arange(N)
-        nip = ipoints * np.exp(2j * np.pi * k / (2 * N))
-        assert np.allclose(nip.imag, 0, atol=1e-9 * max(1.0, float(np.abs(nip).max())))
-        from fractions import Fraction
-        sc = Fraction(self.scale)
-        coeffs = [int(round(Fraction(float(x)) * sc)) for x in nip.real]      # round(BigInt, big(x)*denom) (ckks.jl:38-44)
-        return ring(coeffs)
+        import torch
+        d = torch.from_numpy(np.ascontiguousarray(self.data)).to(f"cuda:{ring.ctx.device}")
+        return RingElement(ring, primal=ring.ctx.ckks_encode(self.scale, d.reshape(1, n))[0])
 
 
 def ckks_mul_plain_vector(a: np.ndarray, c: CipherText) -> CipherText:
