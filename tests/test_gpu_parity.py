@@ -401,7 +401,9 @@ def test_keyswitch_digits(w):
 @pytest.mark.parametrize("N,logqs,w,comps", [(64, [60, 60, 40], 0, 3), (64, [60, 60, 40], 7, 3), (64, [50, 50], 1, 2),
                                              (2048, [50, 50], 1, 3), (1024, [60] * 4, 2, 3),
                                              # N = 2^12, 2^13: base-2^w digits written once and transformed under every prime
-                                             (4096, [60, 60, 40], 2, 3), (4096, [50, 50], 7, 2), (8192, [60, 40, 40], 3, 3)])
+                                             (4096, [60, 60, 40], 2, 3), (4096, [50, 50], 7, 2), (8192, [60, 40, 40], 3, 3),
+                                             # N = 2^15: CRT digits formed inside the first global level of the transform
+                                             (32768, [60, 40, 40], 0, 2), (32768, [60, 40], 0, 3)])
 def test_keyswitch_plain(N, logqs, w, comps):
     qs, psis, ctx, orc = _ring(N, logqs)
     rng = np.random.default_rng(N + w)
@@ -448,6 +450,25 @@ def test_keyswitch_residue_shards_equal_whole(N, logqs, w, comps, world):
             assert np.array_equal(whole[b, 0], w1) and np.array_equal(whole[b, 1], w2)
     with pytest.raises(T.EngineError):
         ctx.keyswitch_shard(T.Context(N, qs[:1], psis[:1]), 1, S.key_rows_for_shard(key_dual, 0, 1), d_ct, w)   # wrong offset
+
+
+def test_keyswitch_modulus_raised_full_size_routes_agree():
+    """BASELINE config 3 shape (N = 2^15, ModulusRaised, CRT digits): the route that forms the digits inside the first
+    global level of the transform equals the route that writes the digit rows and transforms them (kernel generation 1)"""
+    N = 1 << 15
+    qs, psis = T.prime_chain(N, [40, 40, 40, 60, 60])
+    qs, psis = [qs[3]] + qs[:3] + [qs[4]], [psis[3]] + psis[:3] + [psis[4]]            # q0 (60), 3 x 40, special (60)
+    ctx_ct, ctx_ext = T.Context(N, qs[:4], psis[:4]), T.Context(N, qs, psis)
+    rng = np.random.default_rng(15)
+    key_dual = ctx_ext.to_device(_rand(rng, N, qs, (4, 2)))
+    ct = ctx_ct.to_device(_rand(rng, N, qs[:4], (5, 2)))
+    fused = H(ctx_ct.keyswitch(key_dual, ct, 0, ext=ctx_ext))
+    T.ntt_version(1)
+    try:
+        plain = H(ctx_ct.keyswitch(key_dual, ct, 0, ext=ctx_ext))
+    finally:
+        T.ntt_version(3)
+    assert np.array_equal(fused, plain)
 
 
 def test_keyswitch_modulus_raised_matches_python_oracle():

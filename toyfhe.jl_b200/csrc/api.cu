@@ -612,6 +612,10 @@ int tfb_keyswitch_digits(tfb_ctx* c, tfb_ctx* target, uint32_t w, const uint64_t
 static int ks_digits_dual(tfb_ctx* c, tfb_ctx* r, uint32_t w, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch,
                           cudaStream_t st) {
     int rc;
+    if (w == 0) {   // CRT digits of 2^15-position rows: extraction fused with the first global level of the transform
+        rc = launch_ks_crt_ntt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+        if (rc != -1) return rc;
+    }
     bool small = w > 0 && w < 62;
     for (u32 i = 0; small && i < r->L; i++) small = (1ull << w) <= r->q[i];
     if (small && r->L > 1 && r->v3_ok && r->logN >= 12 && r->logN <= 14) {

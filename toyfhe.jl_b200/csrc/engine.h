@@ -69,6 +69,7 @@ struct ProfScope {
 
 // ntt_kernels.cu
 int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
+int launch_ks_crt_ntt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 Dn, u64 batch, cudaStream_t st);
 unsigned long long tfb_launch_count();
 void tfb_count_launch(int n = 1);
 

@@ -279,3 +279,55 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
+
+// ------------------------------------------------- CRT keyswitch digits fused with the first global level (N = 2^15)
+// rlwe_she.jl:326-329: digit k of a ciphertext component is the centred residue modulo q_k, re-embedded in every prime
+// of the target ring.  For rows of 2^15 positions the forward transform starts with one global level anyway; this
+// kernel forms the two embedded operands of each level-1 butterfly directly from the ciphertext row (read once per
+// target prime, from L2) and writes the level's result -- the digit rows are never written out and read back.
+// out [B][Dn][Lt][N]: level 1 applied; the 2^14 sub-block kernels finish the transform.
+__global__ void ks_crt_stage1_kernel(const u64* __restrict__ cend, const u64 ct_stride, u64* __restrict__ out,
+                                     const tw_t* __restrict__ tw_all, const PrimeParams* __restrict__ ppq,
+                                     const PrimeParams* __restrict__ ppt, const u32 Lt, const u32 logN, const u32 k0, const u32 Dn,
+                                     const u64 total) {
+    const u64 gid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (gid >= total) return;
+    const u32 half = 1u << (logN - 1);
+    const u32 i = (u32)(gid & (half - 1));
+    const u64 r = gid >> (logN - 1);          // (b, kk, j)
+    const u32 j = (u32)(r % Lt);
+    const u64 bk = r / Lt;
+    const u64 b = bk / Dn;
+    const u32 k = k0 + (u32)(bk % Dn);
+    const u64 qk = ppq[k].pc.q;
+    const PrimeConst pc = ppt[j].pc;
+    const u64* src = cend + b * ct_stride + ((u64)k << logN) + i;
+    const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(src), c1 = *reinterpret_cast<const ulonglong2*>(src + half);
+    auto embed = [&](const u64 c) {
+        const bool neg = c > (qk >> 1);
+        const u64 mag = neg ? qk - c : c;
+        const u64 v = (qk >> 1) < pc.q ? mag : barrett_red64(mag, pc);   // |digit| <= q_k / 2: no reduction unless the target prime is smaller (uniform branch)
+        return neg ? neg_mod(v, pc.q) : v;
+    };
+    const tw_t w = tw_all[((u64)j << logN) + 1];
+    const u64 X0 = embed(c0.x), X1 = embed(c0.y);
+    const u64 T0 = shoup_full(embed(c1.x), w.w, w.wp, pc.q), T1 = shoup_full(embed(c1.y), w.w, w.wp, pc.q);
+    u64* dst = out + (r << logN) + i;
+    *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(add_mod(X0, T0, pc.q), add_mod(X1, T1, pc.q));
+    *reinterpret_cast<ulonglong2*>(dst + half) = make_ulonglong2(sub_mod(X0, T0, pc.q), sub_mod(X1, T1, pc.q));
+}
+// CRT digit polynomials k0..k0+Dn-1 of `cend` in the NTT domain of ring r (N = 2^15): dig [B][Dn][r->L][N].
+// Returns -1 when the fused route does not apply (the caller extracts the digits and transforms them separately).
+int launch_ks_crt_ntt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 Dn, u64 batch, cudaStream_t st) {
+    if (r->logN != 15 || c->N != r->N || g_ntt_version != 3 || !r->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2) return -1;
+    if (k0 + Dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
+    const u64 rows = batch * Dn * r->L;
+    int rc = ws_reserve(r, (size_t)rows * r->N * sizeof(u64));
+    if (rc) return rc;
+    u64* tmp = (u64*)r->ws;
+    const u64 total = rows << (r->logN - 1);
+    const unsigned tb = 256;
+    { ProfScope ps(PC_KS_DIGITS, st); ks_crt_stage1_kernel<<<(unsigned)((total / 2 + tb - 1) / tb), tb, 0, st>>>(cend, ct_stride, tmp, r->d_fwd, c->d_pp, r->d_pp, r->L, r->logN, k0, Dn, total); }
+    TFB_CUDA(cudaGetLastError());
+    return launch_ntt14p(r, tmp, dig, rows, false, 1, st);
+}

@@ -578,7 +578,7 @@ __global__ void ks_digits_crt_kernel(const u64* __restrict__ cend, const u64 ct_
         const u64 mag = neg ? qi - c : c;
         for (u32 j = 0; j < Lt; j++) {
             const PrimeConst pc = ppt[j].pc;
-            u64 v = barrett_red64(mag, pc);
+            const u64 v = (qi >> 1) < pc.q ? mag : barrett_red64(mag, pc);   // |digit| <= q_i / 2 (uniform branch)
             out[((r * Lt + j) << logN) + n] = neg ? neg_mod(v, pc.q) : v;
         }
     }
