@@ -515,12 +515,6 @@ class CKKSScale:
     scale: float
 
 
-def _zmstar(M: int, row: int, col: int) -> int:
-    """ZmstarPermutation (ckksencoding.jl:47-58), 1-based row/col"""
-    g = pow(3, col, M)
-    return (M - g) % M if row == 2 else g
-
-
 class CKKSEncoding:
     """N/2 complex slots at scale `scale` (ckksencoding.jl:3-9)"""
 
