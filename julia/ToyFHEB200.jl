@@ -16,6 +16,7 @@ module ToyFHEB200
 
 using ToyFHE, StructArrays, OffsetArrays
 using ToyFHE: CRTEncoded
+using ToyFHE: NTT
 using ToyFHE.NTT: NegacyclicRing, RingCoeffs, RingElement, degree, coeffs_primal
 import ToyFHE.NTT: nntt, inntt
 
@@ -106,6 +107,59 @@ function bfv_mul(ℛ, ℛbig, t::Integer, c1::Vector{<:RingElement}, c2::Vector{
     proto = coeffs_primal(c1[1])
     [RingElement{ℛ}(OffsetArray(unpack(proto.parent, out[:, :, k]), axes(proto)...), nothing) for k in 1:3]
 end
+
+# ---- keyswitch with a device-resident evaluation key (rlwe_she.jl:315-347; INTEGRATION.md section 3) ----
+# The evaluation key is uploaded ONCE in the NTT domain ([D][2][L'][N], component 1 = mask, 2 = masked) -- what the
+# reference caches in key.mask.dual / key.masked.dual after first use (pow2_cyc_rings.jl:132-138) -- and every
+# keyswitch then moves only the ciphertext (2-3 polynomials in, 2 out).
+struct DeviceKey
+    ctx::Ptr{Cvoid}          # ring of the ciphertext
+    ext::Ptr{Cvoid}          # raised ring (ModulusRaised) or C_NULL
+    ptr::Ptr{Cvoid}          # device buffer [D][2][L'][N]
+    D::Int
+    w::Int                   # relin_window (0 = CRT digits)
+end
+
+function dmalloc(ctx, bytes)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:tfb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx, bytes, p))
+    p[]
+end
+h2d(ctx, dst, src::Array{UInt64}) = check(ccall((:tfb_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt64}, Csize_t, Ptr{Cvoid}), ctx, dst, src, sizeof(src), C_NULL))
+d2h(ctx, dst::Array{UInt64}, src) = check(ccall((:tfb_memcpy_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), ctx, dst, src, sizeof(dst), C_NULL))
+
+# ek.key :: Vector of (mask, masked) RingElements over ℛkey (rlwe_she.jl:273-298); ℛ = ciphertext ring
+function DeviceKey(ℛ, ℛkey, ek, w::Integer; raised::Bool = ℛkey !== ℛ)
+    kctx = context(ℛkey)
+    D = length(ek.key)
+    host = cat((cat(pack(NTT.coeffs_dual(k.mask).parent), pack(NTT.coeffs_dual(k.masked).parent); dims=3) for k in ek.key)...; dims=4)  # [N, L', 2, D]
+    dev = dmalloc(kctx, sizeof(host))
+    h2d(kctx, dev, host)
+    DeviceKey(context(ℛ), raised ? kctx : C_NULL, dev, D, w)
+end
+
+# c :: Vector of 2 or 3 RingElements over ℛ; returns the 2 components of keyswitch(ek, c)
+function keyswitch(ℛ, dk::DeviceKey, c::Vector{<:RingElement})
+    comps = length(c)
+    host = cat((pack(coeffs_primal(x).parent) for x in c)...; dims=3)       # [N, L, comps]
+    N, L = size(host, 1), size(host, 2)
+    din, dout = dmalloc(dk.ctx, sizeof(host)), dmalloc(dk.ctx, N * L * 2 * 8)
+    h2d(dk.ctx, din, host)
+    check(ccall((:tfb_keyswitch, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt64, Ptr{Cvoid}),
+                dk.ctx, dk.ext, dk.w, dk.ptr, dk.D, din, comps, dout, 1, C_NULL))
+    out = Array{UInt64}(undef, N, L, 2)
+    d2h(dk.ctx, out, dout)
+    check(ccall((:tfb_sync, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dk.ctx, C_NULL))
+    for p in (din, dout)
+        check(ccall((:tfb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dk.ctx, p))
+    end
+    proto = coeffs_primal(c[1])
+    [RingElement{ℛ}(OffsetArray(unpack(proto.parent, out[:, :, k]), axes(proto)...), nothing) for k in 1:2]
+end
+
+# rotate(gk, c) = keyswitch(gk, apply_galois_element(c, g)) (rlwe_she.jl:355-359): the automorphism is
+# tfb_galois on the device buffer between the upload and tfb_keyswitch; same data movement as above.
 
 # BFV plaintext maps (bfv.jl:21-29): Delta * m and mod(divround(SignedMod(x), Delta), t), exact on the device
 limbs(x::Integer) = (n = cld(max(ndigits(x, base=2), 1), 64); UInt64[UInt64((x >> (64 * (i - 1))) & typemax(UInt64)) for i in 1:n])
