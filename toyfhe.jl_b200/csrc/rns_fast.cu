@@ -297,6 +297,10 @@ template <int LN, bool SP, bool ADD>
 __device__ __forceinline__ void garner_fused(const u64 (&r)[LN], u64 (&d)[LN], const GarnerF<LN>& g) {
 #pragma unroll
     for (int i = 0; i < LN; i++) {
+        if (!ADD && i == 0) {   // plain Garner (multiplier 1, no constant): the first digit is the first residue
+            d[0] = r[0];
+            continue;
+        }
         u128 a = (u128)r[i] * g.sc[i];
         if (ADD) a += g.ad[i];
 #pragma unroll
@@ -342,9 +346,9 @@ __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict
     const bool neg = above_half_f<L>(d, T.g);
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        u128 a = 0;
+        u128 a = d[0];          // the weight of the first mixed-radix digit is 1
 #pragma unroll
-        for (int i = 0; i < L; i++) a += (u128)d[i] * T.ev[j * L + i];
+        for (int i = 1; i < L; i++) a += (u128)d[i] * T.ev[j * L + i];
         u64 v = redj<SP>(a, T.pcb[j], T.eb[j]);
         if (neg) v = sub_mod(v, T.qmod[j], T.pcb[j].q);
         out[((p * (L + K) + L + j) << logN) + n] = v;
