@@ -585,6 +585,26 @@ def test_ntt_cluster_pair_kernels(logN, logqs, B):
         T.ntt_pair(False)
 
 
+def test_many_primes_and_conversion_limits():
+    """contexts hold up to 64 primes (transforms and element-wise work are per prime); the exact base conversions stop at
+    32 primes and say so instead of computing something else"""
+    N = 4096
+    qs, psis = T.prime_chain(N, [60] * 24 + [50] * 16)
+    assert len(qs) == 40
+    ctx, orc = T.Context(N, qs, psis), CO.Rns(N, qs, psis)
+    rng = np.random.default_rng(40)
+    a = _rand(rng, N, qs, (3,))
+    d = ctx.to_device(a)
+    f = ctx.ntt_fwd(d)
+    assert np.array_equal(H(f), orc.nntt(a))
+    assert np.array_equal(H(ctx.ntt_inv(f)), a)
+    assert np.array_equal(H(ctx.ring_mul(d, d)), orc.ring_mul(a, a))
+    with pytest.raises(T.EngineError):
+        ctx.keyswitch_digits(d, 2)                       # 40-prime Garner: unsupported, reported
+    with pytest.raises(T.EngineError):
+        T.Context(N, qs + qs[:30], psis + psis[:30])     # repeated moduli / more than 64 primes
+
+
 def test_non_lazy_primes_take_the_harvey_ladder():
     # PALISADE prime 2^60 - 16383 (src/cryptparams.jl:25) is not of the form 2^b + small: Harvey path
     q, N, psi = 1152921504606830593, 2048, 811032584449645127
