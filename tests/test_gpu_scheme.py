@@ -87,6 +87,26 @@ def test_bfv_simd_replay():
     assert got == [int(x) * int(y) % t for x, y in zip(a, b)]
 
 
+def test_bfv_triv_replay():
+    """test/bfv_triv.jl (BASELINE configs[0]) over its word-size equivalent: N = 2^12, ONE 60-bit prime, t = 53,
+    big ring of three further chain primes; decrypt(c)[0] == 6, decrypt(c*c)[0] == 0x24 mod t"""
+    n = 1 << 12
+    chain = [O.nextprime((1 << 60) + 1, 2 * n)]
+    while len(chain) < 4:
+        chain.append(O.nextprime(chain[-1] + 2 * n, 2 * n))
+    assert chain[0] == 1152921504606904321
+    R, Rbig = T.NegacyclicRing(n, qs=chain[:1]), T.NegacyclicRing(n, qs=chain[1:])
+    params = T.BFVParams(R, Rbig, 53, relin_window=1, sigma=3.2)
+    s = T.Sampler(12)
+    kp = T.keygen(s, params)
+    plain = [0] * n
+    plain[0] = 6
+    c = T.encrypt(s, kp, plain)
+    assert T.decrypt(kp, c)[0] == 6
+    dec = T.decrypt(kp, c * c)
+    assert dec[0] == 0x24 % 53 and not any(dec[1:])
+
+
 def test_bfv_crt_replay_with_device_sampler():
     """test/bfv_crt.jl with every random draw of keygen / encrypt made on the device (tfb_sample_*): nothing but the
     6 and the decrypted 36 crosses the host boundary"""
