@@ -152,6 +152,10 @@ int tfb_bfv_mul(tfb_ctx* ctx_q, tfb_ctx* ctx_big, uint64_t t, const uint64_t* c1
 int tfb_bfv_encode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* m, uint64_t* out, uint64_t polys, void* stream);
 int tfb_bfv_decode(tfb_ctx* ctx, uint64_t t, const uint64_t* delta_limbs, uint32_t n_limbs, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
 
+/* BGV plaintext map pi (bgv.jl:22-25): mod(SignedMod(b_n), t) per coefficient -- centred lift of signedmod.jl:12-19,
+ * exact.  b [polys][L][N] primal -> out [polys][N] in [0, t).  (pi^-1 is the plain embedding of the plaintext.) */
+int tfb_centered_mod(tfb_ctx* ctx, uint64_t t, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream);
+
 /* ---- CKKS encoding on the device -------------------------
  * The complex-FFT maps of src/ckksencoding.jl between N/2 complex slots (interleaved re, im float64, device memory)
  * and a real-coefficient plaintext polynomial; `scale` is the FixedRational denominator (ckks.jl:30-47).

@@ -2,6 +2,8 @@
 the mirrored host interface + CUDA engine (same parameters, same assertions), and
 ciphertext-level bit-exact parity against the oracle with a shared seeded sampler
 (the reference's tests only pin decrypt-level results)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -105,6 +107,31 @@ def test_bfv_triv_replay():
     assert T.decrypt(kp, c)[0] == 6
     dec = T.decrypt(kp, c * c)
     assert dec[0] == 0x24 % 53 and not any(dec[1:])
+
+
+def test_bgv_triv_replay():
+    """test/bgv_triv.jl: BGV over the PALISADE ring m = 4096 of src/cryptparams.jl:25 (q = 2^60 - 16383..., N = 2048 --
+    not a 2^b + small prime, so the Harvey kernels run), t = 256, sigma = 8/sqrt(2 pi)"""
+    q, n, psi = 1152921504606830593, 2048, 811032584449645127
+    R = T.NegacyclicRing(n, qs=[q], psis=[psi])
+    params = T.BGVParams(R, 256, 8 / math.sqrt(2 * math.pi))
+    s = T.Sampler(31)
+    kp = T.keygen(s, params)
+    plain = [0] * n
+    plain[0] = 6
+    c = T.encrypt(s, kp, plain)
+    assert T.decrypt(kp, c)[0] == 6
+    dec = T.decrypt(kp, c * c)
+    assert dec[0] == 0x24 and not any(dec[1:])
+    # the plaintext map against big-integer arithmetic over an RNS ring (centred lift, negative values, 0, Q-1)
+    R3 = T.NegacyclicRing(64, logqs=[60, 60, 40])
+    Q = R3.modulus()
+    rng = np.random.default_rng(3)
+    xs = [int.from_bytes(rng.bytes(24), "little") % Q for _ in range(64)]
+    xs[:5] = [0, 1, Q - 1, Q // 2, Q // 2 + 1]
+    for t in (256, 53, 65537, (1 << 61) - 1):
+        got = T.BGVParams(R3, t, 3.2).pi(R3(xs))
+        assert got == [(x - Q if x > Q // 2 else x) % t for x in xs]
 
 
 def test_bfv_crt_replay_with_device_sampler():

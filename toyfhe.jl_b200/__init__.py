@@ -14,7 +14,7 @@ __all__ = ["force_generic", "ntt_version", "ntt_force_harvey", "ntt_max_mode", "
            "minimal_primitive_root", "ndigits", "prime_chain", "profile_enable", "profile_read", "build_library"]
 
 from .ring import NegacyclicRing, RingElement, nntt, inntt
-from .scheme import (BFVParams, CKKSEncoding, CKKSParams, CKKSScale, CipherText, DropLastParams, EvalMultKey, GaloisKey,
+from .scheme import (BFVParams, BGVParams, CKKSEncoding, CKKSParams, CKKSScale, CipherText, DropLastParams, EvalMultKey, GaloisKey,
                      KeyComponent, KeyPair, KeySwitchKey, ModulusRaised, PrivKey, PubKey, Sampler, SlotEncoding, UsageError,
                      apply_galois_element, ckks_mul_plain_vector, decrypt, enc_mul, encrypt, encrypt_zero,
                      galois_element_from_steps, keygen, keygen_evalmult, keygen_galois, keyswitch, make_eval_key,

@@ -471,6 +471,12 @@ int tfb_bfv_decode(tfb_ctx* c, uint64_t t, const uint64_t* delta, uint32_t nl, c
     return launch_bfv_decode(c, t, delta, nl, b, out, polys, (cudaStream_t)stream);
 }
 
+int tfb_centered_mod(tfb_ctx* c, uint64_t t, const uint64_t* b, uint64_t* out, uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(b); CHECK_PTR(out);
+    return launch_centered_mod(c, t, b, out, polys, (cudaStream_t)stream);
+}
 int tfb_ckks_encode(tfb_ctx* c, double scale, const double* slots, uint64_t* out, uint64_t polys, void* stream) {
     CHECK_CTX(c);
     if (!polys) return TFB_OK;

@@ -92,6 +92,7 @@ int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, 
                             cudaStream_t st);
 int launch_bfv_encode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* m, u64* out, u64 polys, cudaStream_t st);
 int launch_bfv_decode(tfb_ctx* c, u64 t, const u64* delta, u32 nl, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_centered_mod(tfb_ctx* c, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int build_garner(tfb_ctx* c);
 // ckks_kernels.cu
 int launch_ckks_encode(tfb_ctx* c, double scale, const double* slots, u64* out, u64 polys, cudaStream_t st);

@@ -1048,3 +1048,42 @@ int launch_ckks_lift(tfb_ctx* c, double scale, const u64* in, double* v, u64 pol
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
+
+// ---------------------------------------- BGV plaintext map pi (bgv.jl:22-25): mod(SignedMod(x), t) per coefficient
+// X in [0,Q) from its mixed-radix digits by Horner modulo t (exact integer arithmetic), minus Q mod t when the centred
+// lift is negative (X > floor(Q/2), signedmod.jl:12-19); result in [0, t).
+struct ModTArgs { u64 qt[MAXD]; u64 Qt; };   // q_i mod t, Q mod t
+__global__ void centered_mod_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 L, const u32 logN, const u64 t,
+                                    const GarnerTab g, const PrimeParams* __restrict__ pp, const ModTArgs ma, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 p = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 r[MAXD], d[MAXD];
+    for (u32 i = 0; i < L; i++) r[i] = in[((p * L + i) << logN) + n];
+    garner_digits(r, d, L, g, pp);
+    const bool neg = mr_above_half(d, L, g.halfmr);
+    u64 v = 0;
+    for (int i = (int)L - 1; i >= 0; i--) v = (u64)(((u128)v * ma.qt[i] + d[i] % t) % t);
+    if (neg) v = v >= ma.Qt ? v - ma.Qt : v + t - ma.Qt;
+    out[idx] = v;
+}
+int launch_centered_mod(tfb_ctx* c, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    if (t == 0) { tfb_set_error("centered_mod: modulus must be positive"); return TFB_EINVAL; }
+    if (c->L > MAXD || !c->conv_ok) { tfb_set_error("centered_mod: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    ModTArgs ma;
+    u64 Q = 1 % t;
+    for (u32 i = 0; i < c->L; i++) {
+        ma.qt[i] = c->q[i] % t;
+        Q = (u64)((u128)Q * ma.qt[i] % t);
+    }
+    ma.Qt = Q;
+    const u64 total = polys * c->N;
+    const unsigned tb = 128;
+    const u64 nb = (total + tb - 1) / tb;
+    { ProfScope ps(PC_LEVEL, st); centered_mod_kernel<<<(unsigned)nb, tb, 0, st>>>(in, out, c->L, c->logN, t, garner_of(c), c->d_pp, ma, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}

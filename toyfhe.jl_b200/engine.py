@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
-    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
+    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
     "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
     "tfb_bfv_mul_host", "tfb_rescale_host",
 ]
@@ -275,6 +275,12 @@ class Context:
         B = self._batch(c1, 2)
         out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
         _check(self._lib.tfb_bfv_mul(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        return out
+
+    def centered_mod(self, t: int, b, out=None, stream=None):
+        """mod(SignedMod(b), t) per coefficient (BGV pi, bgv.jl:22-25): b [polys][L][N] -> [polys][N]"""
+        out = self.empty(tuple(b.shape[:-2]) + (self.N,)) if out is None else out
+        _check(self._lib.tfb_centered_mod(self.h, C.c_uint64(int(t)), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
         return out
 
     # -- CKKS encoding (ckksencoding.jl:60-101): slots are complex128 device tensors [polys][N/2]

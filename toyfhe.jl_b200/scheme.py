@@ -143,6 +143,27 @@ class BFVParams(SHEShemeParams):
         return tuple(RingElement(self.R, primal=self.R.ctx.bfv_contract(self.Rbig.ctx, self.t, x.coeffs_primal())) for x in cs)
 
 
+class BGVParams(SHEShemeParams):
+    """src/bgv.jl:5-34: plaintext embedded as is, noise scaled by the plaintext modulus t (ShiftedDiscreteNormal),
+    pi = mod(SignedMod(x), t).  Uses the same ring product as the other schemes; both plaintext maps run on the device."""
+
+    def __init__(self, R: NegacyclicRing, t: int, sigma: float):
+        self.R, self.t, self.sigma = R, int(t), float(sigma)
+
+    def R_cipher(self): return self.R
+    def R_plain(self): return self.t
+
+    def pi_inv(self, plaintext: Sequence[int]) -> RingElement:
+        return self.R([int(m) % self.t for m in plaintext])
+
+    def pi(self, b: RingElement) -> List[int]:
+        ctx = self.R.ctx
+        return [int(v) for v in ctx.to_host(ctx.centered_mod(self.t, b.coeffs_primal()))]
+
+    def noise(self, s): return s.gaussian(self.R, self.sigma) * self.t      # t * DiscreteNormal (bgv.jl:27-33)
+    def secret(self, s): return s.gaussian(self.R, self.sigma)
+
+
 class ModulusRaised(SHEShemeParams):
     """src/modulusraising.jl: the last prime of the key ring is a special prime reserved
     for keys; ciphertexts live on the ring with it dropped."""
