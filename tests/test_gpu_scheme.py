@@ -192,6 +192,26 @@ def _ckks_ring(N, n_primes):
     return T.NegacyclicRing(N, qs=q)
 
 
+def test_ckks_triv_replay():
+    """test/ckks_triv.jl: 2048 slots (N = 4096), scale 2^40, the encoder in isolation (re*re decoded at scale^2), then
+    encrypt / decrypt and a ciphertext square.  The reference borrows a single ~180-bit prime from the BFV estimator;
+    the word-size equivalent is an RNS ring of three 60-bit chain primes (same bit budget)."""
+    N = 4096
+    R = T.NegacyclicRing(N, logqs=[60, 60, 60])
+    scale = 2.0 ** 40
+    x = np.linspace(0.0, 1.0, N // 2)
+    plain = T.CKKSEncoding(scale, x.astype(np.complex128))
+    re = plain.to_ring_element(R)
+    sq = T.CKKSEncoding.from_ring_element(re * re, scale * scale)
+    assert np.allclose(np.real(sq.data), x ** 2, atol=1e-4)
+    params = T.CKKSParams(R, 1, 3.2)
+    s = T.Sampler(41)
+    kp = T.keygen(s, params)
+    c = T.encrypt(s, kp, plain)
+    assert np.allclose(np.real(T.decrypt(kp, c).data), x, atol=1e-4)
+    assert np.allclose(np.real(T.decrypt(kp, c * c).data), x ** 2, atol=1e-4)
+
+
 def test_ckks_modswitch_replay():
     """test/ckks_modswitch.jl"""
     N = 32
