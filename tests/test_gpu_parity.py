@@ -221,6 +221,24 @@ def test_bfv_mul_joint_basis_equals_callers_basis(N, L, Lb, t):
     assert np.array_equal(mid, want)
 
 
+def test_squaring_shortcut_equals_the_general_product():
+    """c*c with one operand buffer (what `c*c` in the reference's tests and the x^2 activation of
+    examples/encrypted_mnist pass): the operand is expanded / transformed once; same result as two distinct buffers"""
+    N, L, Lb, t = 4096, 3, 7, 65537
+    allq, allpsi = T.prime_chain(N, [60] * (L + Lb))
+    qs, psis, qb, psib = allq[:L], allpsi[:L], allq[L:], allpsi[L:]
+    cq, cb = T.Context(N, qs, psis), T.Context(N, qb, psib)
+    rng = np.random.default_rng(8)
+    c = _rand(rng, N, qs, (3, 2))
+    d, d2 = cq.to_device(c), cq.to_device(c)
+    sq = H(cq.bfv_mul(cb, t, d, d))
+    assert np.array_equal(sq, H(cq.bfv_mul(cb, t, d, d2)))
+    assert np.array_equal(sq, CO.bfv_mul(CO.Rns(N, qs, psis), CO.Rns(N, qb, psib), t, c, c))
+    ten = H(cq.ct_tensor(d, d))
+    assert np.array_equal(ten, H(cq.ct_tensor(d, d2)))
+    assert np.array_equal(ten, CO.Rns(N, qs, psis).ct_tensor(c, c))
+
+
 def test_bfv_mul_joint_basis_extreme_residues():
     """the 128-bit sums of the joint-basis kernels are reduced by Solinas folds at bit 60: all-(q-1) operands and
     operands whose tensor values sit at +-Q/2 maximise every accumulation; headline shape (L = 8, K = 9)"""

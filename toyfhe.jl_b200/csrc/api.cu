@@ -429,9 +429,9 @@ static int ct_tensor_dev(tfb_ctx* c, const u64* c1, const u64* c2, u64* out, u64
     int rc = stage_reserve(c, 4 * batch * poly * sizeof(u64));
     if (rc) return rc;
     u64* A = (u64*)c->stage;
-    u64* B = A + 2 * batch * poly;
+    u64* B = c1 == c2 ? A : A + 2 * batch * poly;   // squaring (c*c, rlwe_she.jl:264-266 with one operand): transform once
     if ((rc = launch_ntt(c, c1, A, 2 * batch * c->L, false, st))) return rc;
-    if ((rc = launch_ntt(c, c2, B, 2 * batch * c->L, false, st))) return rc;
+    if (c1 != c2 && (rc = launch_ntt(c, c2, B, 2 * batch * c->L, false, st))) return rc;
     if ((rc = launch_tensor_dual(c, A, B, out, batch, st))) return rc;
     return launch_ntt(c, out, out, 3 * batch * c->L, true, st);
 }
@@ -570,10 +570,11 @@ int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const 
         u64* T = E1 + 4 * ch * polyj;
         for (u64 b0 = 0; b0 < batch; b0 += ch) {
             const u64 nb = batch - b0 < ch ? batch - b0 : ch;
-            u64* E2 = E1 + 2 * nb * polyj;
+            const bool square = c1 == c2;            // c*c: expand and transform the operand once
+            u64* E2 = square ? E1 : E1 + 2 * nb * polyj;
             if ((rc = fast_expand_joint(cq, cb, K, c1 + b0 * 2 * polyq, E1, 2 * nb, st))) return rc;
-            if ((rc = fast_expand_joint(cq, cb, K, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
-            if ((rc = launch_ntt(cj, E1, E1, 4 * nb * cj->L, false, st))) return rc;   // E1 and E2 are contiguous
+            if (!square && (rc = fast_expand_joint(cq, cb, K, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
+            if ((rc = launch_ntt(cj, E1, E1, (square ? 2 : 4) * nb * cj->L, false, st))) return rc;   // E1 and E2 are contiguous
             if ((rc = launch_tensor_dual(cj, E1, E2, T, nb, st))) return rc;
             if ((rc = launch_ntt(cj, T, T, 3 * nb * cj->L, true, st))) return rc;
             if ((rc = fast_contract_joint(cq, cb, K, t, T, out + b0 * 3 * polyq, 3 * nb, st))) return rc;
