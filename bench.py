@@ -316,8 +316,9 @@ def run_ours(args):
                     "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg[dom] // max(1, kernels[dom]["launches"] // K),
                     "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
-                    "note": "61-bit modular butterflies: the FMA (IMAD) pipe is 72% busy at this rate -- pipe-bound before HBM "
-                            "(DESIGN.md section 5, profiles/r01_ncu_bfv_step.txt)"}
+                    "note": "integer work on 61-bit residues: the FMA-heavy (IMAD) pipe is 67% busy in the transforms and 86% in the "
+                            "base conversions at these rates and bounds them before HBM does (DESIGN.md section 5, "
+                            "profiles/r01f_ncu_bfv_step.txt)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
