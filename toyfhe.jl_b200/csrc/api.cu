@@ -657,8 +657,8 @@ int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t polyr = (size_t)r->L * r->N, polyc = (size_t)c->L * c->N;
-    // digit chunk so the materialised digit polys stay below ~1 GiB
-    u32 dch = (u32)((size_t)(1ull << 30) / (batch * polyr * sizeof(u64)));
+    // digit chunk so the materialised digit polynomials stay below 4 GiB (of 180 GB): fewer, longer accumulation passes
+    u32 dch = (u32)((size_t)(4ull << 30) / (batch * polyr * sizeof(u64)));
     if (dch < 1) dch = 1;
     if (dch > Dneed) dch = Dneed;
     int rc = stage_reserve(r, (2 * batch * polyr + (size_t)dch * batch * polyr) * sizeof(u64));
@@ -693,7 +693,7 @@ int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, cons
     if (D < Dneed) { tfb_set_error("keyswitch: evaluation key has too few digit components"); return TFB_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t polyr = (size_t)r->L * r->N, polyc = (size_t)c->L * c->N;
-    u32 dch = (u32)((size_t)(1ull << 30) / (batch * polyr * sizeof(u64)));
+    u32 dch = (u32)((size_t)(4ull << 30) / (batch * polyr * sizeof(u64)));
     if (dch < 1) dch = 1;
     if (dch > Dneed) dch = Dneed;
     int rc = stage_reserve(r, (2 * batch * polyr + (size_t)dch * batch * polyr) * sizeof(u64));
