@@ -327,7 +327,29 @@ struct ExpandJTab {
     u64 qmod[K];     // Q mod p_j
     PrimeConst pcb[K];
     u32 eb[K];       // p_j - 2^60 (SP)
+    // fast route (SP): x = sum_i xi_i (Q/q_i) - v Q with xi_i = r_i (Q/q_i)^-1 mod q_i and v = floor(sum_i xi_i / q_i)
+    u64 hinv[L];     // (Q/q_i)^-1 mod q_i
+    u64 frac[L];     // floor(2^124 / q_i)
+    u64 hev[K * L];  // (Q/q_i) mod p_j
+    u64 nq[K];       // (-Q) mod p_j
 };
+
+// exact route: mixed-radix digits (Garner), sign from the digits of floor(Q/2), evaluation modulo every p_j
+template <int L, int K, bool SP>
+__device__ __noinline__ void expand_exact(const u64 (&r)[L], u64* __restrict__ out, const u64 base, const u32 logN, const ExpandJTab<L, K>& T) {
+    u64 d[L];
+    garner_fused<L, SP, false>(r, d, T.g);
+    const bool neg = above_half_f<L>(d, T.g);
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+        u128 a = d[0];          // the weight of the first mixed-radix digit is 1
+#pragma unroll
+        for (int i = 1; i < L; i++) a += (u128)d[i] * T.ev[j * L + i];
+        u64 v = redj<SP>(a, T.pcb[j], T.eb[j]);
+        if (neg) v = sub_mod(v, T.qmod[j], T.pcb[j].q);
+        out[base + ((u64)j << logN)] = v;
+    }
+}
 
 template <int L, int K, bool SP>
 __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
@@ -336,22 +358,39 @@ __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict
     if (idx >= total) return;
     const u64 p = idx >> logN;
     const u32 n = (u32)(idx & ((1u << logN) - 1));
-    u64 r[L], d[L];
+    u64 r[L];
 #pragma unroll
     for (int i = 0; i < L; i++) {
         r[i] = in[((p * L + i) << logN) + n];
         out[((p * (L + K) + i) << logN) + n] = r[i];
     }
-    garner_fused<L, SP, false>(r, d, T.g);
-    const bool neg = above_half_f<L>(d, T.g);
+    const u64 base = ((p * (L + K) + L) << logN) + n;
+    if (!SP) {
+        expand_exact<L, K, SP>(r, out, base, logN, T);
+        return;
+    }
+    // Fast exact conversion.  sum_i xi_i / q_i = v + x/Q with x in [0,Q); the centred lift is x - Q iff x/Q > 1/2, so the
+    // multiple of Q to remove is v' = floor(sum_i xi_i / q_i + 1/2).  Each fraction is taken to 60 bits, rounded DOWN by
+    // less than 2 units: the 60-bit sum U under-estimates by less than 2L units, so floor(U / 2^60) is v' unless U sits
+    // within 2L units below a multiple of 2^60 -- then (probability ~2^-55 per coefficient) the exact route decides.
+    u64 xi[L];
+    u64 U = 1ull << 59;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        xi[i] = redj<true>((u128)r[i] * T.hinv[i], T.g.pc[i], T.g.e[i]);
+        U += __umul64hi(xi[i], T.frac[i]);
+    }
+    if ((U & ((1ull << 60) - 1)) >= (1ull << 60) - 2 * L - 2) {
+        expand_exact<L, K, SP>(r, out, base, logN, T);
+        return;
+    }
+    const u64 v = U >> 60;
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        u128 a = d[0];          // the weight of the first mixed-radix digit is 1
+        u128 a = (u128)v * T.nq[j];
 #pragma unroll
-        for (int i = 1; i < L; i++) a += (u128)d[i] * T.ev[j * L + i];
-        u64 v = redj<SP>(a, T.pcb[j], T.eb[j]);
-        if (neg) v = sub_mod(v, T.qmod[j], T.pcb[j].q);
-        out[((p * (L + K) + L + j) << logN) + n] = v;
+        for (int i = 0; i < L; i++) a += (u128)xi[i] * T.hev[j * L + i];
+        out[base + ((u64)j << logN)] = redj<true>(a, T.pcb[j], T.eb[j]);
     }
 }
 
@@ -477,6 +516,19 @@ static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u
             fill_eval(t.ev + j * L, L, cq, cb->q[j], &t.qmod[j]);
             t.pcb[j] = h_prime_const(cb->q[j]);
             t.eb[j] = (u32)(cb->q[j] - (1ull << 60));
+            t.nq[j] = t.qmod[j] ? cb->q[j] - t.qmod[j] : 0;
+            for (int i = 0; i < L; i++) {   // (Q/q_i) mod p_j
+                u64 M = 1 % cb->q[j];
+                for (int m = 0; m < L; m++) if (m != i) M = h_mulmod(M, cq->q[m] % cb->q[j], cb->q[j]);
+                t.hev[j * L + i] = M;
+            }
+        }
+        for (int i = 0; i < L; i++) {
+            const u64 qi = cq->q[i];
+            u64 M = 1 % qi;                 // (Q/q_i) mod q_i
+            for (int m = 0; m < L; m++) if (m != i) M = h_mulmod(M, cq->q[m] % qi, qi);
+            t.hinv[i] = h_invmod(M, qi);
+            t.frac[i] = qi > (1ull << 60) ? (u64)((((u128)1) << 124) / qi) : 0;   // only used on 2^60 + e primes (SP)
         }
         it = cache.emplace(key, t).first;
     }
