@@ -160,7 +160,12 @@ def test_bfv_switch_contract_mul(N, L, Lb, t, B):
     rng = np.random.default_rng(N + L)
     c1, c2 = _rand(rng, N, qs, (B, 2)), _rand(rng, N, qs, (B, 2))
     Q, Qb = math.prod(qs), math.prod(qb)
-    for k, X in enumerate([Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]):   # strict '>' rule, bfv.jl:202-220
+    # values at and around the centring boundary, including both sides of the window (|x/Q - 1/2| ~ 2L 2^-60) inside which
+    # the fast expansion hands over to the exact Garner route
+    edge = [Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]
+    for sh in (54, 55, 56, 57, 58, 59, 61):
+        edge += [(Q >> 1) + (Q >> sh), (Q >> 1) - (Q >> sh), (Q >> 1) + 1 + (Q >> sh)]
+    for k, X in enumerate(edge):   # strict '>' rule, bfv.jl:202-220
         for i, q in enumerate(qs):
             c1[0, 0, i, k] = X % q
     e1 = H(cq.bfv_switch(cb, cq.to_device(c1)))
@@ -201,7 +206,12 @@ def test_bfv_mul_joint_basis_equals_callers_basis(N, L, Lb, t):
     rng = np.random.default_rng(7 * N + L)
     c1, c2 = _rand(rng, N, qs, (3, 2)), _rand(rng, N, qs, (3, 2))
     Q = math.prod(qs)
-    for k, X in enumerate([Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]):
+    # values at and around the centring boundary, including both sides of the window (|x/Q - 1/2| ~ 2L 2^-60) inside which
+    # the fast expansion hands over to the exact Garner route
+    edge = [Q >> 1, (Q >> 1) + 1, 0, Q - 1, 1, (Q >> 1) - 1]
+    for sh in (54, 55, 56, 57, 58, 59, 61):
+        edge += [(Q >> 1) + (Q >> sh), (Q >> 1) - (Q >> sh), (Q >> 1) + 1 + (Q >> sh)]
+    for k, X in enumerate(edge):
         for i, q in enumerate(qs):
             c1[0, 0, i, k] = X % q
             c2[1, 1, i, (k * 5) % N] = X % q
