@@ -214,8 +214,11 @@ static long long emu3_inv(u64 q, u64 psi, const u64* in, u64* out) {
     typedef NttGeo<R> Geo;
     if (!prime_ok(q)) return -1;
     redent_t tab[16];
+    u64 tab8[16];
     fill_redtab(tab, q);
-    const Red3 rp = make_red3(q, floor_log2(q), tab);
+    fill_redtab8(tab8, q);
+    Red3 rp = make_red3(q, floor_log2(q), tab);
+    rp.tab8 = tab8;
     HostTables ht;
     build_tables(Geo::N, q, psi, ht);
     std::vector<tw_t> invc(Geo::N);
@@ -284,8 +287,11 @@ extern "C" long long emu_ntt3_pair_inv(u64 q, u64 psi, const u64* in, u64* out) 
     typedef NttGeo<R> Geo;
     if (!prime_ok(q)) return -1;
     redent_t tab[16];
+    u64 tab8[16];
     fill_redtab(tab, q);
-    const Red3 rp = make_red3(q, floor_log2(q), tab);
+    fill_redtab8(tab8, q);
+    Red3 rp = make_red3(q, floor_log2(q), tab);
+    rp.tab8 = tab8;
     const u64 Nrow = (u64)Geo::N * 2;
     HostTables ht;
     build_tables(Nrow, q, psi, ht);

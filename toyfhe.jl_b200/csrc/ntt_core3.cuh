@@ -43,7 +43,9 @@ struct __align__(16) redent_t {
 struct Red3 {
     u64 q, q4;
     u32 ne, shb;          // 2^32 - e, b - 32
-    const redent_t* tab;  // this prime's 16 entries
+    const redent_t* tab;  // this prime's 16 entries (forward ladder: c2 and c3 = c2 + 4q in one 128-bit load)
+    const u64* tab8;      // inverse ladder: c2 alone, 8-byte entries -- the 16 entries cover 128 bytes, so lanes with
+                          // different k never collide on a bank (16-byte entries put k and k+8 on the same banks)
 };
 TFB_HD void fill_redtab(redent_t* tab, const u64 q) {
     for (u32 k = 0; k < 16; k++) {
@@ -59,7 +61,11 @@ TFB_HD Red3 make_red3(const u64 q, const u32 b, const redent_t* tab) {
     r.ne = 0u - (u32)(q - (1ull << b));
     r.shb = b - 32;
     r.tab = tab;
+    r.tab8 = nullptr;
     return r;
+}
+TFB_HD void fill_redtab8(u64* tab8, const u64 q) {
+    for (u32 k = 0; k < 16; k++) tab8[k] = q - (u64)k * q;
 }
 // host-side eligibility of one prime (api.cu decides per context)
 static inline bool prime_ok(const u64 q) {
@@ -117,6 +123,7 @@ TFB_HD void levels3(u64* x, const tw_t* __restrict__ tw, const u32* tb, const Re
 }
 // any v < 16 * 2^b -> canonical
 TFB_HD u64 canon3(const u64 v, const Red3& rp) { return csub(v + rp.tab[top4(v, rp)].c2, rp.q); }
+TFB_HD u64 canon3i(const u64 v, const Red3& rp) { return csub(v + rp.tab8[top4(v, rp)], rp.q); }   // inverse kernels (8-byte table)
 
 // pass 1 (levels 1..5): thread t holds a = 0..31 at index t; canonical input, bound 1 -> 13 -> (reduce) 6 -> 10
 template <int R>
@@ -234,7 +241,7 @@ TFB_HD void gs_bfly3(u64& X, u64& Y, const tw_t w, const Red3& rp) {
 #ifndef __CUDA_ARCH__
         if (k > 15) { g_emu_overflow3++; return; }
 #endif
-        X = x + y + rp.tab[k].c2;
+        X = x + y + rp.tab8[k];
 #ifndef __CUDA_ARCH__
         if (X >= 3 * rp.q) g_emu_overflow3++;
 #endif
@@ -330,7 +337,7 @@ TFB_HD void inv_pass1_compute_store(u64* x, u64* __restrict__ orow, const tw_t* 
         x[k + 16] = shoup_lazy4(U - V + rp.q4, twn.w, twn.wp, rp.q, rp.ne, rp.shb);
     }
 #pragma unroll
-    for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = canon3(x[a], rp);
+    for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = canon3i(x[a], rp);
 }
 // ------------------------------------------------------------------ rows of 2^(11+R) positions as a PAIR of sub-blocks
 // (thread-block cluster of two CTAs, ntt_v3_kernels.cuh: each CTA holds one sub-block in its shared memory and reads
@@ -403,6 +410,6 @@ template <int R>
 TFB_HD void inv_cross_finish(u64* x, u64* __restrict__ ohalf, const tw_t tw, const Red3& rp, const u32 t) {
     typedef NttGeo<R> Geo;
 #pragma unroll
-    for (int a = 0; a < 32; a++) ohalf[a * Geo::T + t] = canon3(shoup_lazy4(x[a], tw.w, tw.wp, rp.q, rp.ne, rp.shb), rp);
+    for (int a = 0; a < 32; a++) ohalf[a * Geo::T + t] = canon3i(shoup_lazy4(x[a], tw.w, tw.wp, rp.q, rp.ne, rp.shb), rp);
 }
 }  // namespace v3

@@ -91,7 +91,7 @@ ntt_inv_pair_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_
                     const PrimeParams* __restrict__ pp, const u32 L, const u32 nrows) {
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
-    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    __shared__ u64 redtab8[TFB_MAX_L * 16];
     u32 t = threadIdx.x;
     const u32 rank = cluster_rank();
     const u64* peer = map_peer(smem, rank ^ 1);
@@ -102,7 +102,7 @@ ntt_inv_pair_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    build_redtab(redtab, pp, L, t, Geo::T);
+    build_redtab8(redtab8, pp, L, t, Geo::T);
     __syncthreads();
     if (t == 0 && unit < nrows) {
         mbar_expect_tx(&bar, Geo::N * 8);
@@ -114,7 +114,8 @@ ntt_inv_pair_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_
         asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
         const u32 prime = (u32)(unit % L);
         const tw_t* tw = tw_all + (u64)prime * nrow;
-        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, nullptr);
+        rp.tab8 = redtab8 + prime * 16;
         mbar_wait(&bar, parity);
         parity ^= 1;
         cluster_arrive();

@@ -57,6 +57,14 @@ __device__ __forceinline__ void build_redtab(v3::redent_t* redtab, const PrimePa
     }
 }
 
+__device__ __forceinline__ void build_redtab8(u64* redtab8, const PrimeParams* __restrict__ pp, const u32 L, const u32 t, const u32 nthreads) {
+#pragma unroll 1
+    for (u32 i = t; i < L * 16; i += nthreads) {
+        const u64 q = pp[i >> 4].pc.q;
+        redtab8[i] = q - (u64)(i & 15) * q;
+    }
+}
+
 template <int R, bool S0ZERO>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
@@ -113,14 +121,14 @@ ntt_inv_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
-    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    __shared__ u64 redtab8[TFB_MAX_L * 16];
     u32 t = threadIdx.x;
     u32 unit = blockIdx.x;
     if (t == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    build_redtab(redtab, pp, L, t, Geo::T);
+    build_redtab8(redtab8, pp, L, t, Geo::T);
     __syncthreads();
     if (t == 0 && unit < nunits) {
         mbar_expect_tx(&bar, Geo::N * 8);
@@ -132,7 +140,8 @@ ntt_inv_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
         const u32 prime = (u32)(unit % L);
         const tw_t* tw = tw_all + (u64)prime * Geo::N;
-        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, nullptr);
+        rp.tab8 = redtab8 + prime * 16;
         mbar_wait(&bar, parity);
         parity ^= 1;
         v3::inv_pass3_load<R>(x, smem, t);
@@ -162,10 +171,10 @@ ntt_inv_sub_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
                    const PrimeParams* __restrict__ pp, const u32 L, const u32 s0, const u32 nunits) {
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
-    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    __shared__ u64 redtab8[TFB_MAX_L * 16];
     u32 t = threadIdx.x;
     const u64 nrow = (u64)Geo::N << s0;
-    build_redtab(redtab, pp, L, t, Geo::T);
+    build_redtab8(redtab8, pp, L, t, Geo::T);
     __syncthreads();
     u64 x[32];
     for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
@@ -174,7 +183,8 @@ ntt_inv_sub_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
         const u32 blk = unit & ((1u << s0) - 1);
         const u32 prime = (u32)(row % L);
         const tw_t* tw = tw_all + (u64)prime * nrow;
-        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, nullptr);
+        rp.tab8 = redtab8 + prime * 16;
         {
             const u32 w = t >> 5, lane = t & 31;
             const u64* irow = in + row * nrow + brev_bits(blk, (int)s0);
@@ -193,7 +203,7 @@ ntt_inv_sub_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t
         v3::inv_pass1_levels_all(x, tw, rp, s0, blk);
         u64* orow = out + row * nrow + (u64)blk * Geo::N;
 #pragma unroll
-        for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = v3::canon3(x[a], rp);
+        for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = v3::canon3i(x[a], rp);
     }
 }
 
