@@ -48,10 +48,23 @@ def workload_name(batch):
             f"R_big=17x60-bit primes, batch={batch} ciphertext pairs per GPU")
 
 
-def rings():
-    import toyfhe_b200 as T
-    allq, allpsi = T.prime_chain(N_RING, [60] * (L_Q + L_BIG))
+def rings(reference=False):
+    """primes / roots of NegacyclicRing(2^14, ntuple(_->60, 25)) (crt.jl:282-295).  The reference arm takes them from the
+    oracle's own constructor so that it never loads the engine's library."""
+    if reference:
+        from oracle import toyfhe_oracle as O
+        allq, allpsi = O.prime_chain(N_RING, [60] * (L_Q + L_BIG))
+    else:
+        import toyfhe_b200 as T
+        allq, allpsi = T.prime_chain(N_RING, [60] * (L_Q + L_BIG))
     return allq[:L_Q], allpsi[:L_Q], allq[L_Q:], allpsi[L_Q:]
+
+
+def config_dict(batch):
+    """the same `config` on both arms (the driver compares them)"""
+    Nb = N_RING * 8
+    return {"workload": workload_name(batch), "sharding": "independent ciphertext pairs per GPU, no data-path collective",
+            "l2": f"inputs {2 * batch * 2 * L_Q * Nb / 2**20:.0f} MiB + R_big intermediates per step, far larger than the 126 MB L2 (no flush needed)"}
 
 
 def rand_ct(rng, qs, shape):
@@ -67,7 +80,9 @@ def cpu_bfv_mul_rate(pairs_per_step, steps, warmup):
     """times the oracle's C restatement of the reference path on the host cores"""
     import numpy as np
     from oracle import c_oracle as CO
-    qs, psis, qb, psib = rings()
+    # all host threads, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    CO.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    qs, psis, qb, psib = rings(reference=True)
     oq, ob = CO.Rns(N_RING, qs, psis), CO.Rns(N_RING, qb, psib)
     rng = np.random.default_rng(0)
     c1, c2 = rand_ct(rng, qs, (pairs_per_step, 2)), rand_ct(rng, qs, (pairs_per_step, 2))
@@ -84,15 +99,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pairs = 2
-    value, s_per_step, cores = cpu_bfv_mul_rate(pairs, max(1, args.steps), max(0, min(args.warmup, 1)))
+    pairs = 2   # bounded sample of the workload per step (the rate is per pair, so it compares with the GPU arm's)
+    value, s_per_step, cores = cpu_bfv_mul_rate(pairs, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "sample": f"{pairs} ciphertext pairs per step"},
+        "config": config_dict(args.batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{pairs} pairs x {args.steps} steps; C restatement of the Julia path (oracle/oracle.c), OpenMP"},
+                         "sample": f"{pairs} ciphertext pairs per step x {args.steps} steps (+{args.warmup} warm-up) of the same workload; "
+                                   "C restatement of the Julia path (oracle/oracle.c), OpenMP on all host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -331,8 +347,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(B), "sharding": "independent ciphertext pairs per GPU, no data-path collective",
-                   "l2": f"inputs {2 * B * 2 * L_Q * Nb / 2**20:.0f} MiB + R_big intermediates per step, far larger than the 126 MB L2 (no flush needed)"},
+        "config": config_dict(B),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * 2 * L_Q * Nb),

@@ -59,8 +59,8 @@ int tfb_profile_read(unsigned long long* counts, double* total_ms, int reset);
  * where a register-resident specialisation exists (on = 1), or keep the specialised kernels but reduce 128-bit sums with
  * the generic Shoup/Barrett step instead of the Solinas folds used on 2^60 + e primes (on = 2); all must agree bit for bit */
 int tfb_debug_force_generic(int on);
-/* kernel selection hook for N >= 2^14: 1 = one CTA per row (512 threads x 32 residues), 2 = persistent TMA-prefetched
- * 1024x16 kernels, 3 (default) = persistent TMA-prefetched 512x32 kernels */
+/* kernel selection hook (testing): 1 = one CTA per row (512 threads x 32 residues, ntt_core.cuh),
+ * 3 (default) = persistent TMA-prefetched third-generation kernels; both must agree bit for bit */
 int tfb_debug_ntt_version(int v);
 /* testing hook: force the Harvey (conditional subtract per level) forward ladder even when every prime
  * qualifies for the lazy ladder */
@@ -68,11 +68,6 @@ int tfb_debug_ntt_force_harvey(int on);
 /* testing hook: cap the forward-ladder range policy (0 = Harvey, 1 = lazy, 2 = lazy + approximate quotient,
  * the default when every prime is 2^60 + e with e < 2^28); all must agree bit for bit */
 int tfb_debug_ntt_max_mode(int m);
-/* kernel selection hook for N = 2^15 / 2^16: 1 = hold a row as a pair of 2^14 sub-blocks in a thread-block cluster of
- * two CTAs and run the coupling level through distributed shared memory (ntt_kernels5.cu); 0 (default) = global
- * passes for the coupling levels.  Measured equal (forward) or slower (inverse) on B200 -- DSMEM moves ~20 B/clk/SM,
- * the same as one SM's share of HBM -- so it is kept as a checked alternative only; both must agree bit for bit. */
-int tfb_debug_ntt_pair(int on);
 
 /* ---- ring construction helpers (host only, no GPU needed) ---------------- */
 /* NegacyclicRing(N, logqs) prime chain, crt.jl:282-295: ascending-logq order,

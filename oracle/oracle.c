@@ -389,8 +389,17 @@ void orc_bfv_switch(u64 N, int Lf, const u64 *qf, int Lt, const u64 *qt, const u
     free(bf);
 }
 
-/* mul_contract (bfv.jl:35-40,172-190): in [polys][Lb][N] over qb; y = rha(t*x, Q);
- * out [polys][L][N] = y mod q_i  (switch back to R) */
+/* mul_contract (bfv.jl:35-40): switch(R, multround(e, t, Q)) per coefficient, in [polys][Lb][N] over qb.
+ * Transcribes, line by line:
+ *   multround(SignedMod(x), t, Q) = div(e * t, Q, RoundNearestTiesAway)          bfv.jl:172-174, 188
+ *   e * t = SignedMod{T}(e.x * T(t))   -- the product is taken IN THE CRT FIELD  signedmod.jl:24-28
+ *           (residue-wise modulo every prime of R_big, i.e. modulo Q_big), only then
+ *   convert(Integer, e) = centred lift modulo Q_big                              signedmod.jl:12-19
+ *   div(.., Q, RoundNearestTiesAway), oftype(e, y) = y mod Q_big                 signedmod.jl:30-32, div_hacks.jl:120-135
+ *   switch(R, .) = centred lift modulo Q_big again, then mod q_i                 bfv.jl:202-226
+ * It equals rha(t*centre(x), Q) only while t*|x| < Q_big/2; beyond that the reference wraps modulo Q_big
+ * (it does on test/bfv_crt.jl's 2+4-prime ring) and so does this.
+ * out [polys][L][N] = y mod q_i */
 void orc_bfv_contract(u64 N, int L, const u64 *q, int Lb, const u64 *qb, u64 t, const u64 *in, u64 *out, long polys) {
     basis_t *bq = (basis_t *)malloc(sizeof(basis_t)), *bb = (basis_t *)malloc(sizeof(basis_t));
     basis_init(bq, L, q); basis_init(bb, Lb, qb);
@@ -398,16 +407,15 @@ void orc_bfv_contract(u64 N, int L, const u64 *q, int Lb, const u64 *qb, u64 t, 
     for (long u = 0; u < polys * (long)N; u++) {
         long p = u / N; u64 k = u % N;
         u64 res[BN]; big_t X, Y, R, twoR;
-        for (int j = 0; j < Lb; j++) res[j] = in[(p * Lb + j) * N + k];
+        for (int j = 0; j < Lb; j++) res[j] = mulmod(in[(p * Lb + j) * N + k] % qb[j], t % qb[j], qb[j]);   /* e.x * T(t) */
         basis_reconstruct(bb, res, &X);
         int neg = basis_centre(bb, &X);
-        big_mul_word(&X, t);
         big_divrem(&X, &bq->Q, &Y, &R);
         /* RoundNearestTiesAway (div_hacks.jl:120-135): |r| >= Q/2 rounds away */
         twoR = R; big_add(&twoR, &R);
         if (big_cmp(&twoR, &bq->Q) >= 0) { big_t one; big_set(&one, 1); big_add(&Y, &one); }
-        /* multround re-encodes y in R_big, switch() centred-lifts it again: |y| < Q_big/2
-         * always holds (t < Q), so the final residues are y mod q_i */
+        /* |y| <= Q_big/(2Q) + 1 < Q_big/2, so the second centred lift returns y itself and the final
+         * residues are y mod q_i */
         for (int i = 0; i < L; i++) {
             u64 r = big_mod_word(&Y, q[i]);
             out[(p * L + i) * N + k] = (neg && r) ? q[i] - r : r;

@@ -356,16 +356,22 @@ def bfv_mul_expand(ct, qs, qs_big):
 
 
 def bfv_multround(poly, qs_big, t: int, Q: int):
-    """multround(e, t, q) on an R_big element (bfv.jl:172-190): per coefficient
-    centred lift x, y = rha(t x, Q), re-encoded in the big basis."""
+    """multround(e, t, q) on an R_big element (bfv.jl:182-190 -> :172-174), per coefficient:
+
+        multround(SignedMod(x), t, Q) = div(SignedMod(x) * t, Q, RoundNearestTiesAway).x
+
+    ``SignedMod(x) * t`` is ``SignedMod{T}(x * T(t))`` (signedmod.jl:24-28): the product is taken in the
+    CRT field, i.e. modulo Q_big, BEFORE the centred lift of ``div`` (signedmod.jl:12-19, 30-32);
+    ``oftype(e, y)`` then re-encodes y modulo Q_big.  Equal to rha(t*centre(x), Q) only while
+    t*|x| < Q_big/2 (false on test/bfv_crt.jl's 2+4-prime ring, where the reference wraps)."""
     Qb = math.prod(qs_big)
     N = len(poly[0])
     out = [[0] * N for _ in qs_big]
     for n in range(N):
-        x = centre(crt_reconstruct([poly[j][n] for j in range(len(qs_big))], qs_big), Qb)
-        y = rha(t * x, Q)
+        tx = [(poly[j][n] * (t % p)) % p for j, p in enumerate(qs_big)]       # e.x * T(t), residue-wise
+        y = rha(centre(crt_reconstruct(tx, qs_big), Qb), Q)                     # div(convert(Integer, e), Q, RNTA)
         for j, p in enumerate(qs_big):
-            out[j][n] = y % p
+            out[j][n] = y % p                                                   # oftype(e, y)
     return out
 
 

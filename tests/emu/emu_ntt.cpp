@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "../../toyfhe.jl_b200/csrc/ntt_core.cuh"
-#include "../../toyfhe.jl_b200/csrc/ntt_core2.cuh"
 #include "../../toyfhe.jl_b200/csrc/ntt_core3.cuh"
 #include "../../toyfhe.jl_b200/csrc/tables.h"
 
@@ -101,83 +100,6 @@ extern "C" int emu_bank_conflicts(int R) {
     return -1;
 }
 
-// ---- second-generation kernel (1024 threads x 16 residues, N = 2^14 sub-blocks)
-// Execution order mirrors the CUDA kernel's synchronisation: middle passes run warp
-// by warp (all 32 lanes load, then all 32 lanes store: only __syncwarp between),
-// __syncthreads between passes.  A cross-warp hazard would show up as a mismatch.
-template <int MODE>
-static int run2(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out);
-extern "C" int emu_ntt2(int mode, int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
-    return mode ? run2<1>(inverse, q, psi, s0, in, out) : run2<0>(inverse, q, psi, s0, in, out);
-}
-template <int MODE>
-static int run2(int inverse, u64 q, u64 psi, u32 s0, const u64* in, u64* out) {
-    using namespace v2;
-    const RedParams rp = make_red(q, log2floor(q));
-    const u64 Nrow = (u64)N << s0;
-    HostTables ht;
-    build_tables(Nrow, q, psi, ht);
-    std::vector<u64> smem(N), regs((size_t)T * 16);
-    for (u32 blk = 0; blk < (1u << s0); blk++) {
-        if (!inverse) {
-            memcpy(smem.data(), in + (u64)blk * N, N * sizeof(u64));  // what the TMA bulk copy delivers
-            for (int k = 0; k < 3; k++)
-                for (u32 w = 0; w < T / 32; w++) {
-                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); fwd_mid_load(&regs[t * 16], smem.data(), c); }
-                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); fwd_mid_compute<MODE>(&regs[t * 16], ht.fwd.data(), c, rp); fwd_mid_store(&regs[t * 16], smem.data(), c); }
-                }
-            for (u32 t = 0; t < T; t++) fwd_last_load(&regs[t * 16], smem.data(), t);
-            for (u32 t = 0; t < T; t++) fwd_last_compute_store<MODE>(&regs[t * 16], out, ht.fwd.data(), rp, t, s0, blk);
-        } else {
-            // s0 == 0: the row is first copied flat into shared memory; s0 > 0: gathered from global
-            const u64* src = in;
-            std::vector<u64> flat;
-            if (s0 == 0) { flat.assign(in, in + N); src = flat.data(); }
-            for (u32 t = 0; t < T; t++) inv_first_load(&regs[t * 16], src, t, s0, blk);
-            for (u32 t = 0; t < T; t++) inv_first_compute_store(&regs[t * 16], smem.data(), ht.inv.data(), q, t, s0, blk);
-            for (int k = 2; k >= 1; k--)
-                for (u32 w = 0; w < T / 32; w++) {
-                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); inv_mid_load(&regs[t * 16], smem.data(), c); }
-                    for (u32 l = 0; l < 32; l++) { u32 t = w * 32 + l; PassCfg c = make_cfg(k, t, s0, blk); inv_mid_compute(&regs[t * 16], ht.inv.data(), c, q); inv_mid_store(&regs[t * 16], smem.data(), c); }
-                }
-            for (u32 t = 0; t < T; t++) { PassCfg c = make_cfg(0, t, s0, blk); inv_mid_load(&regs[t * 16], smem.data(), c); }
-            for (u32 t = 0; t < T; t++) { PassCfg c = make_cfg(0, t, s0, blk); inv_final_compute_store(&regs[t * 16], out + (u64)blk * N, ht.inv.data(), c, q, t, s0, ht.ninv, ht.ninv_w1); }
-        }
-    }
-    return 0;
-}
-
-// worst 8-byte-bank conflict degree over all shared-memory access patterns of v2
-extern "C" int emu_bank_conflicts2() {
-    using namespace v2;
-    int worst = 1;
-    auto census = [&](u32* addr) {
-        for (int h = 0; h < 2; h++) {
-            int cnt[16] = {0};
-            for (int l = 0; l < 16; l++) cnt[addr[h * 16 + l] % 16]++;
-            for (int i = 0; i < 16; i++) worst = cnt[i] > worst ? cnt[i] : worst;
-        }
-    };
-    u32 addr[32];
-    for (u32 w = 0; w < T / 32; w++) {
-        for (int k = 0; k < 3; k++)
-            for (int r = 0; r < 16; r++) {
-                for (u32 l = 0; l < 32; l++) { PassCfg c = make_cfg(k, w * 32 + l, 0, 0); addr[l] = (u32)(r >> 2) * c.S4 + c.wl[r & 3]; }
-                census(addr);
-                for (u32 l = 0; l < 32; l++) { PassCfg c = make_cfg(k, w * 32 + l, 0, 0); addr[l] = (u32)(r >> 2) * c.S4 + c.ws[r & 3]; }
-                census(addr);
-            }
-        for (int g = 0; g < 4; g++)
-            for (int e = 0; e < 4; e++) {
-                for (u32 l = 0; l < 32; l++) addr[l] = last_slot(last_rest(w * 32 + l, g), e);
-                census(addr);
-                for (u32 l = 0; l < 32; l++) addr[l] = (brev_bits((u32)e, 2) << 12) | ((u32)g * T + w * 32 + l);  // inverse: flat natural read
-                census(addr);
-            }
-    }
-    return worst;
-}
-
 // ---- third-generation kernels (ntt_core3.cuh): skewed row buffer, approximate quotient, fused reductions.
 // Return the number of lazy-range violations (must be 0), -1 if the prime is not eligible.
 static u32 floor_log2(u64 q) { u32 b = 0; while (b < 63 && (q >> (b + 1))) b++; return b; }
@@ -245,80 +167,6 @@ extern "C" long long emu_ntt3_inv(int R, u64 q, u64 psi, const u64* in, u64* out
     if (R == 3) return emu3_inv<3>(q, psi, in, out);
     if (R == 2) return emu3_inv<2>(q, psi, in, out);
     return -2;
-}
-
-// rows of 2^15 as a pair of sub-blocks (cluster of two CTAs exchanging through distributed shared memory)
-extern "C" long long emu_ntt3_pair_fwd(u64 q, u64 psi, const u64* in, u64* out) {
-    using namespace v3;
-    constexpr int R = 4;
-    typedef NttGeo<R> Geo;
-    if (!prime_ok(q)) return -1;
-    redent_t tab[16];
-    fill_redtab(tab, q);
-    const Red3 rp = make_red3(q, floor_log2(q), tab);
-    const u64 Nrow = (u64)Geo::N * 2;
-    HostTables ht;
-    build_tables(Nrow, q, psi, ht);
-    std::vector<tw_t> fwdc(Nrow);
-    permute_pass3(ht.fwd.data(), fwdc.data(), 15);
-    std::vector<u64> smem[2], regs[2];
-    g_emu_overflow3 = 0;
-    for (u32 r = 0; r < 2; r++) {
-        smem[r].assign(Lay<R>::ROW_WORDS, 0);
-        regs[r].assign((size_t)Geo::T * 32, 0);
-        for (u32 a = 0; a < 32; a++) memcpy(&smem[r][slot<R>(a, 0)], in + (u64)r * Geo::N + a * Geo::T, Geo::T * 8);
-    }
-    for (u32 r = 0; r < 2; r++)
-        for (u32 t = 0; t < Geo::T; t++) {
-            pass1_cross_load<R>(&regs[r][t * 32], smem[r].data(), smem[1 - r].data(), r, ht.fwd[1], rp, t);
-            pass1_cross_levels(&regs[r][t * 32], ht.fwd.data(), rp, 1, r);
-        }
-    for (u32 r = 0; r < 2; r++) {
-        for (u32 t = 0; t < Geo::T; t++) pass1_store<R>(&regs[r][t * 32], smem[r].data(), t);
-        for (u32 t = 0; t < Geo::T; t++) pass2<R>(&regs[r][t * 32], smem[r].data(), ht.fwd.data(), rp, t, 1, r);
-        for (u32 t = 0; t < Geo::T; t++) pass3_load<R>(&regs[r][t * 32], smem[r].data(), t);
-        for (u32 t = 0; t < Geo::T; t++) pass3_compute_store<R, false>(&regs[r][t * 32], out, fwdc.data(), rp, t, 1, r);
-    }
-    return (long long)g_emu_overflow3;
-}
-extern "C" long long emu_ntt3_pair_inv(u64 q, u64 psi, const u64* in, u64* out) {
-    using namespace v3;
-    constexpr int R = 4;
-    typedef NttGeo<R> Geo;
-    if (!prime_ok(q)) return -1;
-    redent_t tab[16];
-    u64 tab8[16];
-    fill_redtab(tab, q);
-    fill_redtab8(tab8, q);
-    Red3 rp = make_red3(q, floor_log2(q), tab);
-    rp.tab8 = tab8;
-    const u64 Nrow = (u64)Geo::N * 2;
-    HostTables ht;
-    build_tables(Nrow, q, psi, ht);
-    std::vector<tw_t> invc(Nrow);
-    permute_pass3(ht.inv.data(), invc.data(), 15);
-    std::vector<u64> smem[2], regs[2];
-    g_emu_overflow3 = 0;
-    for (u32 r = 0; r < 2; r++) {
-        smem[r].assign(Lay<R>::ROW_WORDS, 0);
-        regs[r].assign((size_t)Geo::T * 32, 0);
-        memcpy(smem[r].data(), in + (u64)r * Geo::N, Geo::N * 8);   // one contiguous half each
-    }
-    for (u32 r = 0; r < 2; r++)
-        for (u32 t = 0; t < Geo::T; t++) inv_pass3_load_pair<R>(&regs[r][t * 32], smem[r].data(), smem[1 - r].data(), r, t);
-    for (u32 r = 0; r < 2; r++) {
-        for (u32 t = 0; t < Geo::T; t++) inv_pass3_compute_store<R>(&regs[r][t * 32], smem[r].data(), invc.data(), rp, t, r);
-        for (u32 t = 0; t < Geo::T; t++) inv_pass2<R>(&regs[r][t * 32], smem[r].data(), ht.inv.data(), rp, t, 1, r);
-        for (u32 t = 0; t < Geo::T; t++) inv_pass1_load<R>(&regs[r][t * 32], smem[r].data(), t);
-        for (u32 t = 0; t < Geo::T; t++) inv_pass1_levels_all(&regs[r][t * 32], ht.inv.data(), rp, 1, r);
-        for (u32 t = 0; t < Geo::T; t++) pass1_store<R>(&regs[r][t * 32], smem[r].data(), t);
-    }
-    for (u32 r = 0; r < 2; r++)
-        for (u32 t = 0; t < Geo::T; t++) {
-            inv_cross_combine<R>(&regs[r][t * 32], smem[1 - r].data(), r, rp, t);
-            inv_cross_finish<R>(&regs[r][t * 32], out + (u64)r * Geo::N, r ? ht.ninv_w1 : ht.ninv, rp, t);
-        }
-    return (long long)g_emu_overflow3;
 }
 
 // bank census of the skewed layout: 64-bit accesses per half-warp (passes 1, 2), 128-bit per quarter-warp (pass 3)

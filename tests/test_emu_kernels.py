@@ -1,5 +1,5 @@
 """CPU-only: run the per-thread bodies of the CUDA NTT kernels (ntt_core.cuh /
-ntt_core2.cuh, compiled as host code in tests/emu) thread by thread and compare
+compiled as host code in tests/emu) thread by thread and compare
 with the oracle.  This checks thread mappings, swizzles, twiddle indices, the
 natural-order stores and the lazy-reduction bounds without a GPU."""
 import ctypes as C
@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 @pytest.fixture(scope="module")
 def emu():
     csrc = os.path.join(os.path.dirname(HERE), "toyfhe.jl_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("ntt_core.cuh", "ntt_core2.cuh", "ntt_core3.cuh", "modarith.cuh", "tables.h")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("ntt_core.cuh", "ntt_core3.cuh", "modarith.cuh", "tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return C.CDLL(LIB)
@@ -91,23 +91,6 @@ def test_v1_row_kernels(emu, R, mode):
         assert np.array_equal(got, want)
         back = np.zeros_like(a)
         emu.emu_ntt(R, mode, 1, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(want), P(back))
-        assert np.array_equal(back, a)
-
-
-@pytest.mark.parametrize("mode", [0, 1])
-def test_v2_row_kernel(emu, mode):
-    N = 1 << 14
-    for logq in (60, 40, 59):
-        q, psi, orc = ring(N, logq)
-        rng = np.random.default_rng(mode)
-        a = rng.integers(0, q, size=(1, N), dtype=np.uint64)
-        a[0, :4] = [q - 1, q - 1, 0, 1]
-        want = orc.nntt(a)
-        got = np.zeros_like(a)
-        emu.emu_ntt2(mode, 0, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(a), P(got))
-        assert np.array_equal(got, want)
-        back = np.zeros_like(a)
-        emu.emu_ntt2(mode, 1, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(want), P(back))
         assert np.array_equal(back, a)
 
 
@@ -193,45 +176,20 @@ def test_v3_kernels_all_sizes_and_prime_widths(emu, R, logq):
             assert np.array_equal(back, orc.inntt(a))
 
 
-@pytest.mark.parametrize("logq", [60, 40])
-def test_v3_pair_kernels_for_rows_of_2_to_15(emu, logq):
-    """N = 2^15 (CKKS config of BASELINE.json) as a pair of sub-blocks: the cross level of the forward transform
-    runs first on the pair, of the inverse last (N^-1 folded in); bit-exact, lazy ranges held"""
-    N = 1 << 15
-    emu.emu_ntt3_pair_fwd.restype = C.c_longlong
-    emu.emu_ntt3_pair_inv.restype = C.c_longlong
-    qs, psis = O.prime_chain(N, (logq,) * 2)
-    q, psi = qs[1], psis[1]
-    orc = CO.Rns(N, [q], [psi])
-    rng = np.random.default_rng(logq)
-    rows = [rng.integers(0, q, size=N, dtype=np.uint64), np.full(N, q - 1, dtype=np.uint64),
-            np.where(np.arange(N) < N // 2, q - 1, 0).astype(np.uint64), np.where(np.arange(N) % 2 == 0, q - 1, 1).astype(np.uint64)]
-    for a in rows:
-        a = np.ascontiguousarray(a.reshape(1, N))
-        got, back = np.zeros_like(a), np.zeros_like(a)
-        assert emu.emu_ntt3_pair_fwd(C.c_uint64(q), C.c_uint64(psi), P(a), P(got)) == 0
-        assert np.array_equal(got, orc.nntt(a))
-        assert emu.emu_ntt3_pair_inv(C.c_uint64(q), C.c_uint64(psi), P(got), P(back)) == 0
-        assert np.array_equal(back, a)
-        assert emu.emu_ntt3_pair_inv(C.c_uint64(q), C.c_uint64(psi), P(a), P(back)) == 0
-        assert np.array_equal(back, orc.inntt(a))
-
-
 def test_worst_case_inputs_lazy_bounds(emu):
     """all-(q-1) rows maximise every lazy intermediate: the lazy ladder must not wrap 2^64"""
     N = 1 << 14
     q, psi, orc = ring(N, 60)
     a = np.full((1, N), q - 1, dtype=np.uint64)
     want = orc.nntt(a)
-    for fn, args in ((emu.emu_ntt2, (1, 0)), (emu.emu_ntt, (4, 1, 0))):
+    for fn, args in ((emu.emu_ntt, (4, 1, 0)),):
         got = np.zeros_like(a)
         fn(*args, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(0), P(a), P(got))
         assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("s0", [1, 2])
-@pytest.mark.parametrize("gen", [1, 2])
-def test_long_rows_as_sub_blocks(emu, s0, gen):
+def test_long_rows_as_sub_blocks(emu, s0):
     N = 1 << (14 + s0)
     q, psi, orc = ring(N, 60)
     rng = np.random.default_rng(s0)
@@ -239,21 +197,14 @@ def test_long_rows_as_sub_blocks(emu, s0, gen):
     want = orc.nntt(a)
     staged = np.ascontiguousarray(fwd_global_stages(a[0], q, psi, s0)).reshape(1, N)
     got = np.zeros_like(a)
-    if gen == 1:
-        emu.emu_ntt(4, 1, 0, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got))
-    else:
-        emu.emu_ntt2(1, 0, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got))
+    emu.emu_ntt(4, 1, 0, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(staged), P(got))
     assert np.array_equal(got, want)
     part = np.zeros_like(a)
-    if gen == 1:
-        emu.emu_ntt(4, 1, 1, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(want), P(part))
-    else:
-        emu.emu_ntt2(1, 1, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(want), P(part))
+    emu.emu_ntt(4, 1, 1, C.c_uint64(q), C.c_uint64(psi), C.c_uint32(s0), P(want), P(part))
     assert np.array_equal(inv_global_stages(part[0], q, psi, s0), a[0])
 
 
 def test_shared_memory_layouts_are_conflict_free(emu):
     assert emu.emu_bank_conflicts(4) == 1      # 512x32 kernel at N = 2^14
-    assert emu.emu_bank_conflicts2() == 1      # 1024x16 kernel
     for R in (2, 3, 4):                        # skewed layout of the third-generation kernels
         assert emu.emu_bank_conflicts3(R) == 1

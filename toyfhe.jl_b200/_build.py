@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libtoyfhe_b200.so")
-SOURCES = ["api.cu", "ntt_kernels.cu", "rns_kernels.cu", "rns_fast.cu", "ntt_kernels2.cu", "ntt_kernels3.cu", "ntt_kernels4.cu", "ntt_kernels5.cu", "sample_kernels.cu", "ckks_kernels.cu"]
-HEADERS = ["engine.h", "modarith.cuh", "ntt_core.cuh", "ntt_core2.cuh", "ntt_core3.cuh", "ntt_v3_kernels.cuh", "tables.h", os.path.join("..", "..", "include", "toyfhe_b200.h")]
+SOURCES = ["api.cu", "ntt_kernels.cu", "rns_kernels.cu", "rns_fast.cu", "ntt_kernels3.cu", "ntt_kernels4.cu", "sample_kernels.cu", "ckks_kernels.cu"]
+HEADERS = ["engine.h", "modarith.cuh", "ntt_core.cuh", "ntt_core3.cuh", "ntt_v3_kernels.cuh", "tables.h", os.path.join("..", "..", "include", "toyfhe_b200.h")]
 
 
 def _stale() -> bool:

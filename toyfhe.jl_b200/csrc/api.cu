@@ -15,10 +15,25 @@ int tfb_cuda_fail(cudaError_t e, const char* what) {
     return TFB_ECUDA;
 }
 
-#define CHECK_CTX(c)                                                  \
-    do {                                                              \
-        if (!(c)) { tfb_set_error("null context"); return TFB_EINVAL; } \
-    } while (0)
+// Every entry point that takes a context runs with that context's device current and restores the caller's device on
+// return (one process may drive several GPUs; contexts are destroyed from garbage collectors at arbitrary points).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define TFB_CAT2(a, b) a##b
+#define TFB_CAT(a, b) TFB_CAT2(a, b)
+#define CHECK_CTX(c)                                                \
+    if (!(c)) { tfb_set_error("null context"); return TFB_EINVAL; } \
+    DeviceGuard TFB_CAT(dg_, __COUNTER__)((c)->device)
 #define CHECK_ROWS(c, rows)                                                                         \
     do {                                                                                            \
         if ((rows) % (c)->L) { tfb_set_error("rows must be a multiple of the number of primes"); return TFB_EINVAL; } \
@@ -116,16 +131,11 @@ int tfb_profile_read(unsigned long long* counts, double* ms, int reset) {
 }
 int tfb_profile_classes(void) { return PC_COUNT; }
 int tfb_debug_ntt_version(int v) {
-    g_ntt_version = (v >= 1 && v <= 3) ? v : 3;
+    g_ntt_version = (v == 1 || v == 3) ? v : 3;
     return TFB_OK;
 }
 int tfb_debug_ntt_max_mode(int m) {
     g_ntt_max_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
-    return TFB_OK;
-}
-int tfb_debug_ntt_pair(int on) {
-    extern bool g_ntt_pair;
-    g_ntt_pair = on != 0;
     return TFB_OK;
 }
 int tfb_debug_ntt_force_harvey(int on) {
@@ -215,7 +225,11 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         for (uint32_t j = 0; j < i; j++)
             if (q[j] == q[i]) { tfb_set_error("ctx_create: repeated modulus"); return TFB_EINVAL; }
     }
-    TFB_CUDA(cudaSetDevice(device));
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); tfb_set_error("ctx_create: no such CUDA device"); return TFB_EINVAL; }
+    }
+    DeviceGuard dg(device);
     tfb_ctx* c = new tfb_ctx();
     static std::atomic<u64> next_uid{1};
     c->uid = next_uid.fetch_add(1);
@@ -272,9 +286,7 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
         rc = tfb_cuda_fail(e, "ctx_create table upload");
     if (!rc) rc = build_garner(c);
     if (!rc) rc = ntt_setup_device();
-    if (!rc) rc = ntt2_setup_device();
     if (!rc) rc = ntt3_setup_device();
-    if (!rc) rc = ntt5_setup_device();
     if (!rc) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
@@ -293,7 +305,7 @@ static void forget_joint(const tfb_ctx* c);
 static void forget_pipe(const tfb_ctx* c);
 int tfb_ctx_destroy(tfb_ctx* c) {
     if (!c) return TFB_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     tfb_forget_ctx_pairs(c);
     forget_joint(c);
     forget_pipe(c);
@@ -322,7 +334,6 @@ int tfb_ctx_info(const tfb_ctx* c, uint32_t* N, uint32_t* L, uint64_t* q, uint64
 int tfb_malloc(tfb_ctx* c, size_t bytes, void** dptr) {
     CHECK_CTX(c);
     CHECK_PTR(dptr);
-    TFB_CUDA(cudaSetDevice(c->device));
     cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
     if (e != cudaSuccess) { cudaGetLastError(); tfb_set_error("out of device memory"); return TFB_ENOMEM; }
     return TFB_OK;

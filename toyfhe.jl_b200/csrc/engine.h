@@ -109,9 +109,6 @@ int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, 
 int fast_contract_joint(tfb_ctx* cq, tfb_ctx* cb, int K, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
 void tfb_forget_ctx_pairs(const tfb_ctx* c);
 int ntt_setup_device();
-// ntt_kernels2.cu
-int ntt2_setup_device();
-int launch_ntt14(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
 // ntt_kernels3.cu
 int ntt3_setup_device();
 int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
@@ -120,10 +117,7 @@ int ntt4_setup_device();
 int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
 int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
-// ntt_kernels5.cu
-int ntt5_setup_device();
-int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);
-int launch_ntt_pair(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u32 s0, cudaStream_t st);
+int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
 extern bool g_ntt_force_harvey;
 extern int g_ntt_max_mode;  // debug cap on the ladder mode (2 = no cap)
-extern int g_ntt_version;  // 1 = 512x32 kernels everywhere, 2 = 1024x16 persistent kernels where available
+extern int g_ntt_version;  // 1 = one CTA per row (ntt_core.cuh), 3 = persistent third-generation kernels (default)

@@ -339,77 +339,11 @@ TFB_HD void inv_pass1_compute_store(u64* x, u64* __restrict__ orow, const tw_t* 
 #pragma unroll
     for (int a = 0; a < 32; a++) orow[a * Geo::T + t] = canon3i(x[a], rp);
 }
-// ------------------------------------------------------------------ rows of 2^(11+R) positions as a PAIR of sub-blocks
-// (thread-block cluster of two CTAs, ntt_v3_kernels.cuh: each CTA holds one sub-block in its shared memory and reads
-// the other's through distributed shared memory).  Global level s0 pairs position p of sub-block 2m (X) with
-// position p of sub-block 2m+1 (Y), twiddle index 2^(s0-1) + m; rank = which sub-block this CTA owns.
-// Forward: the cross level runs first, on canonical input: X' = X + wY, Y' = X - wY + 4q, both < 5q; the five
-// levels of pass 1 then reduce at level 3 (bound 5 -> 9 -> 13 -> (reduce) 6 -> 10 -> 14; pass 2 reduces at its level 1).
-template <int R>
-TFB_HD void pass1_cross_load(u64* x, const u64* own, const u64* peer, const u32 rank, const tw_t wc, const Red3& rp, const u32 t) {
-#pragma unroll
-    for (int a = 0; a < 32; a++) {
-        const u64 mine = own[slot<R>(a, t)], other = peer[slot<R>(a, t)];
-        const u64 X = rank ? other : mine, Y = rank ? mine : other;
-        const u64 tt = shoup_lazy4(Y, wc.w, wc.wp, rp.q, rp.ne, rp.shb);
-#ifndef __CUDA_ARCH__
-        if (tt >= rp.q4 || X >= rp.q) g_emu_overflow3++;
-#endif
-        x[a] = rank ? X - tt + rp.q4 : X + tt;
-    }
-}
-TFB_HD void pass1_cross_levels(u64* x, const tw_t* __restrict__ tw, const Red3& rp, const u32 s0, const u32 blk) {
-    u32 tb[5];
-#pragma unroll
-    for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
-    levels3<5, 0x04>(x, tw, tb, rp);
-}
-template <int R>
-TFB_HD void pass1_store(const u64* x, u64* smem, const u32 t) {
-#pragma unroll
-    for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
-}
-// Inverse, s0 = 1 (the row is exactly the pair): each CTA holds one contiguous HALF of the natural-order row; the
-// sub-block `rank` needs the elements n = 2 kl + rank, i.e. position ((kl mod N/2) << 1 | rank) of half kl div N/2.
-template <int R>
-TFB_HD void inv_pass3_load_pair(u64* x, const u64* own, const u64* peer, const u32 rank, const u32 t) {
-    typedef NttGeo<R> Geo;
-    const u32 w = t >> 5, lane = t & 31;
-    const u64* h0 = rank ? peer : own;   // first half of the row
-    const u64* h1 = rank ? own : peer;   // second half
-#pragma unroll
-    for (int g = 0; g < (int)Geo::G; g++)
-#pragma unroll
-        for (int c = 0; c < (int)Geo::RS; c++) {
-            const u32 kl = (brev_bits((u32)c, R) << 10) | ((Geo::G * w + g) << 5) | lane;
-            const u32 off = ((kl & (Geo::N / 2 - 1)) << 1) | rank;
-            x[g * Geo::RS + c] = (kl >> (Geo::LOGN - 1)) ? h1[off] : h0[off];
-        }
-}
-// levels 5..1 of the sub-block (no N^-1: the cross level is the last one)
+// levels 5..1 of a sub-block of a longer row (no N^-1: the global inverse stages follow)
 TFB_HD void inv_pass1_levels_all(u64* x, const tw_t* __restrict__ itw, const Red3& rp, const u32 s0, const u32 blk) {
     u32 tb[5];
 #pragma unroll
     for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
     gs_levels3<5, 1, true>(x, itw, tb, rp);
-}
-// cross level: rank 0 keeps U + V, rank 1 keeps U - V + 4q (U = sub-block 2m's value, V = sub-block 2m+1's; both < 4q)
-template <int R>
-TFB_HD void inv_cross_combine(u64* x, const u64* peer, const u32 rank, const Red3& rp, const u32 t) {
-#pragma unroll
-    for (int a = 0; a < 32; a++) {
-        const u64 o = peer[slot<R>(a, t)];
-#ifndef __CUDA_ARCH__
-        if (o >= rp.q4 || x[a] >= rp.q4) g_emu_overflow3++;
-#endif
-        x[a] = rank ? o - x[a] + rp.q4 : x[a] + o;
-    }
-}
-// tw = N^-1 (rank 0) or N^-1 psi^-brev(1) (rank 1) when this is the row's last level; canonical natural-order output
-template <int R>
-TFB_HD void inv_cross_finish(u64* x, u64* __restrict__ ohalf, const tw_t tw, const Red3& rp, const u32 t) {
-    typedef NttGeo<R> Geo;
-#pragma unroll
-    for (int a = 0; a < 32; a++) ohalf[a * Geo::T + t] = canon3i(shoup_lazy4(x[a], tw.w, tw.wp, rp.q, rp.ne, rp.shb), rp);
 }
 }  // namespace v3

@@ -15,10 +15,10 @@
 #include "engine.h"
 #include "ntt_core.cuh"
 
-int g_ntt_version = 3;  // 1 = one CTA per row (512x32), 2 = persistent 1024x16 + TMA, 3 = persistent 512x32 + TMA (tools/ntt_compare.py)
+int g_ntt_version = 3;  // 1 = one CTA per row (512x32, ntt_core.cuh), 3 = persistent 512x32 + TMA (ntt_core3.cuh); the 1024x16 generation and the
+                        // cluster-pair kernels of round 1 were measured slower and removed (profiles/r01_ntt_sizes*.txt keep their numbers)
 bool g_ntt_force_harvey = false;
 int g_ntt_max_mode = 2;
-bool g_ntt_pair = false;  // N > 2^14: cluster-pair kernels (ntt_kernels5.cu) instead of global passes for the coupling level
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
 void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
@@ -221,7 +221,6 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
         TFB_CUDA(cudaGetLastError());
         return TFB_OK;
     }
-    if (logN == 14 && g_ntt_version == 2) return launch_ntt14(c, in, out, rows, inverse, 0, st);
     if (logN == 14 && g_ntt_version == 3) return launch_ntt14p(c, in, out, rows, inverse, 0, st);
     if ((logN == 12 || logN == 13) && g_ntt_version == 3) {
         const int rc = launch_ntt_s(c, in, out, rows, inverse, st);
@@ -238,40 +237,18 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     const u64 total = rows << (logN - 1);
     const unsigned tb = 256;
     const unsigned nb = (unsigned)((total / 2 + tb - 1) / tb);   // two butterflies per thread
-    const bool pair = g_ntt_pair && g_ntt_version == 3 && c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2;
     if (!inverse) {
-        // cluster-pair kernel (ntt_kernels5.cu): levels 1..s0-1 as global passes, level s0 inside the pair
-        if (pair) {
-            const u64* src = in;
-            for (u32 s = 1; s + 1 <= s0; s++) {
-                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
-                src = tmp;
-            }
-            TFB_CUDA(cudaGetLastError());
-            rc = launch_ntt_pair(c, src, out, rows, false, s0, st);
-            if (rc != -1) return rc;
-            if (s0 > 1) {   // pair kernel unavailable after all: finish the remaining global level
-                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(tmp, tmp, c->d_fwd, c->d_pp, c->L, logN, s0, total); }
-                TFB_CUDA(cudaGetLastError());
-                return launch_ntt14p(c, tmp, out, rows, false, s0, st);
-            }
-        }
         const u64* src = in;
         for (u32 s = 1; s <= s0; s++) {
             { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
             src = tmp;
         }
         TFB_CUDA(cudaGetLastError());
-        if (g_ntt_version == 2) return launch_ntt14(c, tmp, out, rows, false, s0, st);
         if (g_ntt_version == 3) return launch_ntt14p(c, tmp, out, rows, false, s0, st);
         return launch_row_dispatch(c, 4, tmp, out, rows, false, s0, st);
     }
-    if (pair && s0 == 1) {
-        rc = launch_ntt_pair(c, in, out, rows, true, 1, st);
-        if (rc != -1) return rc;
-    }
     rc = g_ntt_version == 3 ? launch_ntt_inv_sub(c, in, tmp, rows, s0, st) : -1;
-    if (rc == -1) rc = g_ntt_version == 2 ? launch_ntt14(c, in, tmp, rows, true, s0, st) : launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
+    if (rc == -1) rc = launch_row_dispatch(c, 4, in, tmp, rows, true, s0, st);
     if (rc) return rc;
     for (u32 s = s0; s >= 1; s--) {
         { ProfScope ps(PC_NTT_OTHER, st); ntt_inv_stage_kernel<<<nb, tb, 0, st>>>(tmp, s == 1 ? out : tmp, c->d_inv, c->d_pp, c->L, logN, s, total); }

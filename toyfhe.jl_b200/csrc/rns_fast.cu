@@ -9,8 +9,8 @@
 // (__grid_constant__), so after unrolling every Garner / evaluation constant is
 // an immediate c[0x0][..] operand of the IMADs -- no table loads at all.
 //
-// Sub-basis trick in contract: y_abs = floor((t|x| + (Q-1)/2) / Q) is bounded by
-// t*Qb/(2Q) + 1, so it is already determined by its residues modulo the first KB
+// Sub-basis trick in contract: y_abs = floor((|x'| + (Q-1)/2) / Q), x' = centre(t x mod Qb), is bounded by
+// Qb/(2Q) + 1, so it is already determined by its residues modulo the first KB
 // primes of the big basis (host picks the smallest KB with prod_{j<KB} p_j above
 // that bound; the Garner tables of a prefix basis are prefixes of the full ones).
 #include <map>
@@ -99,16 +99,17 @@ __global__ void __launch_bounds__(128) switch_fast_kernel(const u64* __restrict_
 }
 
 // ------------------------------------------------------------------ contract
+// Reference semantics (bfv.jl:172-174 with signedmod.jl:24-32): the multiplication by t happens in the CRT field
+// (residue-wise, modulo Q_big) BEFORE the centred lift:  x' = centre((t X) mod Q_big),  y = rha(x' / Q).
 template <int L, int LB, int KB>
 struct ContractTab {
     GarnerC<LB> gb;
     GarnerC<L> gq;
     u64 ev_bq[L * LB];   // (prod_{m<k} p_m) mod q_i
     u64 pb_mod_q[L];     // Qb mod q_i
-    tw_t t_q[L];         // t mod q_i
     u64 h_q[L];          // (Q-1)/2 mod q_i
     u64 ev_qb[KB * L];   // (prod_{m<i} q_m) mod p_j, j < KB
-    tw_t t_b[KB];        // t mod p_j
+    tw_t t_b[LB];        // t mod p_j
     u64 h_b[KB];         // (Q-1)/2 mod p_j
     tw_t qinv_b[KB];     // Q^-1 mod p_j
 };
@@ -122,17 +123,17 @@ __global__ void __launch_bounds__(128) contract_fast_kernel(const u64* __restric
     const u32 n = (u32)(idx & ((1u << logN) - 1));
     u64 rb[LB], db[LB];
 #pragma unroll
-    for (int j = 0; j < LB; j++) rb[j] = in[((p * LB + j) << logN) + n];
+    for (int j = 0; j < LB; j++)   // e.x * T(t): the product in the field, before any lift
+        rb[j] = shoup_full(in[((p * LB + j) << logN) + n], T.t_b[j].w, T.t_b[j].wp, T.gb.pc[j].q);
     garner_reg<LB, LB>(rb, db, T.gb);
     const bool neg = above_half_reg<LB>(db, T.gb);
-    // a = t|x| + h modulo every q_i, then R = a mod Q in mixed radix over the q basis
+    // a = |x'| + h modulo every q_i, then R = a mod Q in mixed radix over the q basis
     u64 aq[L], dq[L];
 #pragma unroll
     for (int i = 0; i < L; i++) {
         const PrimeConst& pc = T.gq.pc[i];
         u64 v = eval_reg<LB, LB>(db, T.ev_bq + i * LB, pc);
         if (neg) v = sub_mod(T.pb_mod_q[i], v, pc.q);
-        v = shoup_full(v, T.t_q[i].w, T.t_q[i].wp, pc.q);
         aq[i] = add_mod(v, T.h_q[i], pc.q);
     }
     garner_reg<L, L>(aq, dq, T.gq);
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(128) contract_fast_kernel(const u64* __restric
     for (int j = 0; j < KB; j++) {
         const PrimeConst& pc = T.gb.pc[j];
         const u64 xa = neg ? neg_mod(rb[j], pc.q) : rb[j];
-        const u64 a = add_mod(shoup_full(xa, T.t_b[j].w, T.t_b[j].wp, pc.q), T.h_b[j], pc.q);
+        const u64 a = add_mod(xa, T.h_b[j], pc.q);
         const u64 Rj = eval_reg<L, L>(dq, T.ev_qb + j * L, pc);
         rb[j] = shoup_full(sub_mod(a, Rj, pc.q), T.qinv_b[j].w, T.qinv_b[j].wp, pc.q);
     }
@@ -184,10 +185,11 @@ static u64 half_mod(const tfb_ctx* c, u64 m) {  // floor(Q/2) mod m via its mixe
     return h;
 }
 
-// smallest k such that prod_{j<k} p_j > t*Qb/(2Q) + 2  (bit-length estimate, conservative)
+// smallest k such that prod_{j<k} p_j > Qb/(2Q) + 2  (bit-length estimate, conservative): |x'| <= Qb/2 whatever t is,
+// because the product t x is reduced modulo Q_big before the lift
 static int min_sub_basis(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
+    (void)t;
     long double need = 2.0L;  // slack bits
-    need += log2l((long double)t);
     for (u32 j = 0; j < cb->L; j++) need += log2l((long double)cb->q[j]);
     for (u32 i = 0; i < cq->L; i++) need -= log2l((long double)cq->q[i]);
     long double have = 0;
@@ -236,14 +238,13 @@ static int run_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
         for (int i = 0; i < L; i++) {
             const u64 qi = cq->q[i];
             fill_eval(T.ev_bq + i * LB, LB, cb, qi, &T.pb_mod_q[i]);
-            T.t_q[i] = h_tw(t % qi, qi);
             T.h_q[i] = half_mod(cq, qi);
         }
+        for (int j = 0; j < LB; j++) T.t_b[j] = h_tw(t % cb->q[j], cb->q[j]);
         for (int j = 0; j < KB; j++) {
             const u64 pj = cb->q[j];
             u64 Qm;
             fill_eval(T.ev_qb + j * L, L, cq, pj, &Qm);
-            T.t_b[j] = h_tw(t % pj, pj);
             T.h_b[j] = half_mod(cq, pj);
             T.qinv_b[j] = h_tw(h_invmod(Qm, pj), pj);
         }
@@ -457,10 +458,10 @@ static int joint_basis_size(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
     long double logQ = 0, logP = 0;
     for (u32 i = 0; i < cq->L; i++) logQ += log2l((long double)cq->q[i]);
     for (u32 k = 0; k < cb->L; k++) logP += log2l((long double)cb->q[k]);
-    // The caller's big ring must itself hold every tensor value without wrap-around (P > N Q^2);
-    // otherwise the reference's result depends on P (centred lift modulo P, bfv.jl:202-226) and
-    // only the conversion over the caller's own basis reproduces it.
-    if (logP <= (long double)cq->logN + 2 * logQ + 0.01L) return 0;
+    // The caller's big ring must itself hold t times every tensor value without wrap-around (P > t N Q^2): the
+    // reference multiplies by t modulo P before the centred lift (signedmod.jl:24-32, bfv.jl:172-174), so below that
+    // bound its result depends on P and only the conversion over the caller's own basis reproduces it.
+    if (logP <= log2l((long double)t) + (long double)cq->logN + 2 * logQ + 0.01L) return 0;
     const long double need = 2.0L + 0.01L + log2l((long double)t) + (long double)cq->logN + logQ;
     long double have = 0;
     for (u32 k = 0; k < cb->L; k++) {

@@ -480,14 +480,15 @@ int launch_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 
     return TFB_OK;
 }
 
-// ------------------------- mul_contract (bfv.jl:35-40, 172-190): y = rha(t x, Q) mod q_i
-// in [P][Lb][N] over the big basis (x centred in Q_big), out [P][L][N].
-// Exact, all in word arithmetic:  |x| = X or Qb - X;  a = t|x| + (Q-1)/2;  R = a mod Q
+// ------------------------- mul_contract (bfv.jl:35-40, 172-190)
+// in [P][Lb][N] over the big basis, out [P][L][N].  The reference's multround(SignedMod(x), t, Q) multiplies by t IN THE
+// CRT FIELD (SignedMod{T}(x * T(t)), signedmod.jl:24-28), i.e. residue-wise modulo Q_big, and only then takes the
+// centred lift and divides (signedmod.jl:30-32, bfv.jl:172-174):  x' = centre((t X) mod Q_big),  y = rha(x' / Q).
+// Exact, all in word arithmetic:  r_j <- t r_j mod p_j;  |x'| = X' or Qb - X';  a = |x'| + (Q-1)/2;  R = a mod Q
 // (known through its residues a mod q_i);  y_abs = (a - R)/Q computed modulo every
 // p_j, converted back to the q_i basis;  sign restored at the end.  For odd Q,
-// floor((t|x| + (Q-1)/2)/Q) is exactly round-half-away (div_hacks.jl:120-135).
+// floor((|x'| + (Q-1)/2)/Q) is exactly round-half-away (div_hacks.jl:120-135).  y_abs <= Qb/(2Q) + 1 < Qb for any t.
 struct ContractArgs {
-    tw_t t_q[MAXD];  // t mod q_i
     tw_t t_b[MAXD];  // t mod p_j
 };
 __global__ void bfv_contract_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 L, const u32 Lb,
@@ -501,28 +502,28 @@ __global__ void bfv_contract_kernel(const u64* __restrict__ in, u64* __restrict_
     const u64 p = idx >> logN;
     const u32 n = (u32)(idx & (N - 1));
     u64 rb[MAXD], db[MAXD], aq[MAXD], dq[MAXD];
-    for (u32 j = 0; j < Lb; j++) rb[j] = in[((p * Lb + j) << logN) + n];
+    for (u32 j = 0; j < Lb; j++)   // e.x * T(t): the product in the field, before any lift
+        rb[j] = shoup_full(in[((p * Lb + j) << logN) + n], ca.t_b[j].w, ca.t_b[j].wp, ppb[j].pc.q);
     garner_digits(rb, db, Lb, gb, ppb);
     const bool neg = mr_above_half(db, Lb, gb.halfmr);
-    // a mod q_i = t |x| + h
+    // a mod q_i = |x'| + h
     for (u32 i = 0; i < L; i++) {
         const PrimeConst pc = ppq[i].pc;
-        u64 v = mr_eval(db, Lb, b2q.ev + (size_t)i * Lb, pc);  // X mod q_i
-        if (neg) v = sub_mod(b2q.qmod[i], v, pc.q);             // (Qb - X) mod q_i
-        v = shoup_full(v, ca.t_q[i].w, ca.t_q[i].wp, pc.q);
+        u64 v = mr_eval(db, Lb, b2q.ev + (size_t)i * Lb, pc);  // X' mod q_i
+        if (neg) v = sub_mod(b2q.qmod[i], v, pc.q);             // (Qb - X') mod q_i
         aq[i] = add_mod(v, hq[i], pc.q);
     }
     // R = a mod Q, mixed radix over the q basis
     garner_digits(aq, dq, L, gq, ppq);
-    // y_abs mod p_j = (t|x| + h - R) Q^-1
+    // y_abs mod p_j = (|x'| + h - R) Q^-1
     for (u32 j = 0; j < Lb; j++) {
         const PrimeConst pc = ppb[j].pc;
         const u64 xa = neg ? neg_mod(rb[j], pc.q) : rb[j];
-        const u64 a = add_mod(shoup_full(xa, ca.t_b[j].w, ca.t_b[j].wp, pc.q), q2b.hmod[j], pc.q);
+        const u64 a = add_mod(xa, q2b.hmod[j], pc.q);
         const u64 Rj = mr_eval(dq, L, q2b.ev + (size_t)j * L, pc);
         rb[j] = shoup_full(sub_mod(a, Rj, pc.q), q2b.qinv[j].w, q2b.qinv[j].wp, pc.q);
     }
-    // y_abs back to the q basis (y_abs < Q_big because t < Q)
+    // y_abs back to the q basis
     garner_digits(rb, db, Lb, gb, ppb);
     for (u32 i = 0; i < L; i++) {
         const PrimeConst pc = ppq[i].pc;
@@ -546,7 +547,6 @@ int launch_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out
     if ((rc = get_pair(cq, cb, &q2b))) return rc;
     if ((rc = get_pair(cq, cq, &q2q))) return rc;
     ContractArgs ca;
-    for (u32 i = 0; i < cq->L; i++) ca.t_q[i] = h_tw(t % cq->q[i], cq->q[i]);
     for (u32 j = 0; j < cb->L; j++) ca.t_b[j] = h_tw(t % cb->q[j], cb->q[j]);
     const u64 total = polys * cq->N;
     const unsigned tb = 128;

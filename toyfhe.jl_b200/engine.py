@@ -22,7 +22,7 @@ _lib = None
 ABI_SYMBOLS = [
     "tfb_last_error", "tfb_version", "tfb_kernel_launches",
     "tfb_profile_enable", "tfb_profile_classes", "tfb_profile_class_name", "tfb_profile_read",
-    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode", "tfb_debug_ntt_pair",
+    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode",
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
@@ -72,7 +72,7 @@ def force_generic(on) -> None:
 
 
 def ntt_version(v: int) -> None:
-    """testing hook: select the row-kernel generation (1 or 2)"""
+    """testing hook: select the row-kernel generation (1 = one CTA per row, 3 = persistent third generation, the default)"""
     _check(load_library().tfb_debug_ntt_version(C.c_int(int(v))))
 
 
@@ -84,11 +84,6 @@ def ntt_force_harvey(on: bool) -> None:
 def ntt_max_mode(m: int) -> None:
     """testing hook: cap the forward ladder's range policy (0 Harvey, 1 lazy, 2 lazy + approximate quotient)"""
     _check(load_library().tfb_debug_ntt_max_mode(C.c_int(int(m))))
-
-
-def ntt_pair(on: bool) -> None:
-    """testing hook: N = 2^15 / 2^16 rows as cluster pairs exchanging through distributed shared memory"""
-    _check(load_library().tfb_debug_ntt_pair(C.c_int(1 if on else 0)))
 
 
 def profile_enable(on: bool) -> None:
@@ -141,10 +136,11 @@ def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
-def _stream_ptr(stream) -> C.c_void_p:
+def _stream_ptr(stream, device=None) -> C.c_void_p:
+    """``stream`` or torch's current stream OF THE CONTEXT'S DEVICE (not of whatever device happens to be current)"""
     if stream is None:
         import torch
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
     return C.c_void_p(stream.cuda_stream)
 
 
@@ -203,18 +199,18 @@ class Context:
     # -- transforms
     def ntt_fwd(self, a, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out
-        _check(self._lib.tfb_ntt_fwd(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ntt_fwd(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def ntt_inv(self, a, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out
-        _check(self._lib.tfb_ntt_inv(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ntt_inv(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def _bin(self, fn, a, b, out, stream):
         assert a.shape == b.shape
         out = self.empty(a.shape) if out is None else out
-        _check(fn(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(fn(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def add(self, a, b, out=None, stream=None): return self._bin(self._lib.tfb_add, a, b, out, stream)
@@ -224,29 +220,29 @@ class Context:
 
     def neg(self, a, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out
-        _check(self._lib.tfb_neg(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_neg(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def scalar_mul(self, a, s: int, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out
         sr = (C.c_uint64 * self.L)(*[int(s) % q for q in self.qs])
-        _check(self._lib.tfb_scalar_mul(self.h, _ptr(a), sr, _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_scalar_mul(self.h, _ptr(a), sr, _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def galois(self, a, g: int, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out
-        _check(self._lib.tfb_galois(self.h, C.c_uint64(int(g)), _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_galois(self.h, C.c_uint64(int(g)), _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     # -- level changes
     def rescale(self, a, out=None, stream=None):
         out = self.empty(tuple(a.shape[:-2]) + (self.L - 1, self.N)) if out is None else out
-        _check(self._lib.tfb_rescale(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_rescale(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out
 
     def crt_expand(self, a, P: int, out=None, stream=None):
         out = self.empty(tuple(a.shape[:-2]) + (self.L + 1, self.N)) if out is None else out
-        _check(self._lib.tfb_crt_expand(self.h, C.c_uint64(int(P)), _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_crt_expand(self.h, C.c_uint64(int(P)), _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out
 
     # -- ciphertext multiply
@@ -258,56 +254,56 @@ class Context:
     def ct_tensor(self, c1, c2, out=None, stream=None):
         B = self._batch(c1, 2)
         out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
-        _check(self._lib.tfb_ct_tensor(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        _check(self._lib.tfb_ct_tensor(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_switch(self, to: "Context", a, out=None, stream=None):
         out = to.empty(tuple(a.shape[:-2]) + (to.L, to.N)) if out is None else out
-        _check(self._lib.tfb_bfv_switch(self.h, to.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_switch(self.h, to.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_contract(self, big: "Context", t: int, a, out=None, stream=None):
         out = self.empty(tuple(a.shape[:-2]) + (self.L, self.N)) if out is None else out
-        _check(self._lib.tfb_bfv_contract(self.h, big.h, C.c_uint64(int(t)), _ptr(a), _ptr(out), C.c_uint64(big._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_contract(self.h, big.h, C.c_uint64(int(t)), _ptr(a), _ptr(out), C.c_uint64(big._polys(a)), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_mul(self, big: "Context", t: int, c1, c2, out=None, stream=None):
         B = self._batch(c1, 2)
         out = self.empty(tuple(c1.shape[:-3]) + (3, self.L, self.N)) if out is None else out
-        _check(self._lib.tfb_bfv_mul(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_mul(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
     def centered_mod(self, t: int, b, out=None, stream=None):
         """mod(SignedMod(b), t) per coefficient (BGV pi, bgv.jl:22-25): b [polys][L][N] -> [polys][N]"""
         out = self.empty(tuple(b.shape[:-2]) + (self.N,)) if out is None else out
-        _check(self._lib.tfb_centered_mod(self.h, C.c_uint64(int(t)), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
+        _check(self._lib.tfb_centered_mod(self.h, C.c_uint64(int(t)), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream, self.device)))
         return out
 
     # -- CKKS encoding (ckksencoding.jl:60-101): slots are complex128 device tensors [polys][N/2]
     def ckks_encode(self, scale: float, slots, out=None, stream=None):
         polys = int(slots.numel() // (self.N // 2))
         out = self.empty(tuple(slots.shape[:-1]) + (self.L, self.N)) if out is None else out
-        _check(self._lib.tfb_ckks_encode(self.h, C.c_double(float(scale)), C.c_void_p(slots.data_ptr()), _ptr(out), C.c_uint64(polys), _stream_ptr(stream)))
+        _check(self._lib.tfb_ckks_encode(self.h, C.c_double(float(scale)), C.c_void_p(slots.data_ptr()), _ptr(out), C.c_uint64(polys), _stream_ptr(stream, self.device)))
         return out
 
     def ckks_decode(self, scale: float, a, out=None, stream=None):
         import torch
         if out is None:
             out = torch.empty(tuple(a.shape[:-2]) + (self.N // 2,), dtype=torch.complex128, device=a.device)
-        _check(self._lib.tfb_ckks_decode(self.h, C.c_double(float(scale)), _ptr(a), C.c_void_p(out.data_ptr()), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ckks_decode(self.h, C.c_double(float(scale)), _ptr(a), C.c_void_p(out.data_ptr()), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out
 
     # -- sampling on the device (poly.jl:7-23)
     def sample_uniform(self, seed: int, stream_id: int, polys_shape=(1,), out=None, stream=None):
         out = self.empty(tuple(polys_shape) + (self.L, self.N)) if out is None else out
         _check(self._lib.tfb_sample_uniform(self.h, C.c_uint64(int(seed)), C.c_uint32(int(stream_id)), _ptr(out),
-                                            C.c_uint64(self._polys(out)), _stream_ptr(stream)))
+                                            C.c_uint64(self._polys(out)), _stream_ptr(stream, self.device)))
         return out
 
     def sample_gaussian(self, sigma: float, seed: int, stream_id: int, polys_shape=(1,), out=None, stream=None):
         out = self.empty(tuple(polys_shape) + (self.L, self.N)) if out is None else out
         _check(self._lib.tfb_sample_gaussian(self.h, C.c_double(float(sigma)), C.c_uint64(int(seed)), C.c_uint32(int(stream_id)),
-                                             _ptr(out), C.c_uint64(self._polys(out)), _stream_ptr(stream)))
+                                             _ptr(out), C.c_uint64(self._polys(out)), _stream_ptr(stream, self.device)))
         return out
 
     # -- BFV plaintext maps (bfv.jl:21-29)
@@ -325,14 +321,14 @@ class Context:
         arr, n = self._limbs(delta)
         polys = int(m.numel() // self.N)
         out = self.empty(tuple(m.shape[:-1]) + (self.L, self.N)) if out is None else out
-        _check(self._lib.tfb_bfv_encode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_encode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_decode(self, t: int, delta: int, b, out=None, stream=None):
         """b [polys][L][N] primal -> mod(divround(SignedMod(b), Delta), t) [polys][N]"""
         arr, n = self._limbs(delta)
         out = self.empty(tuple(b.shape[:-2]) + (self.N,)) if out is None else out
-        _check(self._lib.tfb_bfv_decode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_decode(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream, self.device)))
         return out
 
     # -- key switching
@@ -341,7 +337,7 @@ class Context:
         D = self.L if w == 0 else ndigits(self.qs, w)
         B = self._polys(cend)
         out = self.empty(tuple(cend.shape[:-2]) + (D, target.L, self.N)) if out is None else out
-        _check(self._lib.tfb_keyswitch_digits(self.h, target.h, C.c_uint32(w), _ptr(cend), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+        _check(self._lib.tfb_keyswitch_digits(self.h, target.h, C.c_uint32(w), _ptr(cend), _ptr(out), C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
     def keyswitch(self, key_dual, ct, w: int, ext: Optional["Context"] = None, out=None, stream=None):
@@ -351,7 +347,7 @@ class Context:
         D = key_dual.shape[0]
         out = self.empty(tuple(ct.shape[:-3]) + (2, self.L, self.N)) if out is None else out
         _check(self._lib.tfb_keyswitch(self.h, ext.h if ext is not None else None, C.c_uint32(w), _ptr(key_dual),
-                                       C.c_uint32(D), _ptr(ct), C.c_uint32(comps), _ptr(out), C.c_uint64(B), _stream_ptr(stream)))
+                                       C.c_uint32(D), _ptr(ct), C.c_uint32(comps), _ptr(out), C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
     def keyswitch_shard(self, shard: "Context", first: int, key_dual_shard, ct, w: int, out=None, stream=None):
@@ -361,42 +357,42 @@ class Context:
         out = shard.empty(tuple(ct.shape[:-3]) + (2, shard.L, self.N)) if out is None else out
         _check(self._lib.tfb_keyswitch_shard(self.h, shard.h, C.c_uint32(first), C.c_uint32(w), _ptr(key_dual_shard),
                                              C.c_uint32(key_dual_shard.shape[0]), _ptr(ct), C.c_uint32(comps), _ptr(out),
-                                             C.c_uint64(B), _stream_ptr(stream)))
+                                             C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
     # -- host-buffer entry points (numpy uint64 or pinned torch tensors)
     def ntt_fwd_host(self, a, out, stream=None):
-        _check(self._lib.tfb_ntt_fwd_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ntt_fwd_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def ntt_inv_host(self, a, out, stream=None):
-        _check(self._lib.tfb_ntt_inv_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ntt_inv_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def ring_mul_host(self, a, b, out, stream=None):
-        _check(self._lib.tfb_ring_mul_host(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ring_mul_host(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
         return out
 
     def ct_tensor_host(self, c1, c2, out, stream=None):
-        _check(self._lib.tfb_ct_tensor_host(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream)))
+        _check(self._lib.tfb_ct_tensor_host(self.h, _ptr(c1), _ptr(c2), _ptr(out), C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_mul_host(self, big: "Context", t: int, c1, c2, out, stream=None):
         _check(self._lib.tfb_bfv_mul_host(self.h, big.h, C.c_uint64(int(t)), _ptr(c1), _ptr(c2), _ptr(out),
-                                          C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream)))
+                                          C.c_uint64(self._batch(c1, 2)), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_encode_host(self, t: int, delta: int, m, out, stream=None):
         arr, n = self._limbs(delta)
         polys = int((m.numel() if hasattr(m, "numel") else m.size) // self.N)
-        _check(self._lib.tfb_bfv_encode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_encode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(m), _ptr(out), C.c_uint64(polys), _stream_ptr(stream, self.device)))
         return out
 
     def bfv_decode_host(self, t: int, delta: int, b, out, stream=None):
         arr, n = self._limbs(delta)
-        _check(self._lib.tfb_bfv_decode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream)))
+        _check(self._lib.tfb_bfv_decode_host(self.h, C.c_uint64(int(t)), arr, C.c_uint32(n), _ptr(b), _ptr(out), C.c_uint64(self._polys(b)), _stream_ptr(stream, self.device)))
         return out
 
     def rescale_host(self, a, out, stream=None):
-        _check(self._lib.tfb_rescale_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream)))
+        _check(self._lib.tfb_rescale_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out

@@ -64,7 +64,23 @@ class Sampler:
 # scheme parameters (rlwe_she.jl:9-65)
 # ----------------------------------------------------------------------------
 class SHEShemeParams:
+    """Parameter objects compare STRUCTURALLY: the reference's checks are ``c1.params !== c2.params`` on immutable
+    structs (rlwe_she.jl:223-225, 233, 248), i.e. egality by value -- two ``DropLastParams`` built by separate
+    ``modswitch`` calls around the same parameters are the same parameters (examples/encrypted_mnist/infer.jl:137-160
+    adds and multiplies such ciphertexts)."""
     relin_window: int = 0
+
+    def _key(self):
+        return (type(self),) + tuple(sorted((k, v) for k, v in self.__dict__.items()))
+
+    def __eq__(self, other):
+        return isinstance(other, SHEShemeParams) and type(self) is type(other) and self.__dict__ == other.__dict__
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.relin_window))
 
     def R_cipher(self) -> NegacyclicRing: raise NotImplementedError
     def R_key(self) -> NegacyclicRing: return self.R_cipher()
@@ -259,7 +275,7 @@ class CipherText:
 
     def _addsub(self, other, sub: bool):
         if isinstance(other, CipherText):
-            if other.params is not self.params:
+            if other.params != self.params:
                 raise UsageError("Attempting to add ciphertexts with differing parameters")
             n = max(len(self), len(other))
             out = []
@@ -388,7 +404,7 @@ def decrypt(key, c: CipherText):
 # homomorphic multiplication (rlwe_she.jl:247-266)
 # ----------------------------------------------------------------------------
 def enc_mul(c1: CipherText, c2: CipherText):
-    if c1.params is not c2.params:
+    if c1.params != c2.params:
         raise UsageError("Attempting to multiply ciphertexts with differing parameters")
     params = c1.params
     # the hooks are looked up on `params` itself: PassthroughParams such as ModulusRaised do
