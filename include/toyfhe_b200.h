@@ -109,6 +109,11 @@ int tfb_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, u
 int tfb_neg(tfb_ctx* ctx, const uint64_t* a, uint64_t* out, uint64_t rows, void* stream);
 /* scalar_mul (pow2_cyc_rings.jl:177-185); s_residues = HOST array [L], s mod q_i */
 int tfb_scalar_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* s_residues, uint64_t* out, uint64_t rows, void* stream);
+/* plaintext multiply broadcast over a batch: out[p] (+)= a[p] (.) plain for p < polys, a/out [polys][L][N], plain [L][N],
+ * all in the same domain (dual for a ring product).  Replaces `map(c -> c * re, c.cs)` of the CKKS plaintext-vector
+ * multiply (ckksencoding.jl:106-111) over every ciphertext of a batch, and with accumulate != 0 the `result += ...` of
+ * the diagonal-method matmuls (test/ckks_matmul.jl:34-42, examples/encrypted_mnist/infer.jl:142-151). */
+int tfb_mul_plain(tfb_ctx* ctx, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, int accumulate, void* stream);
 
 /* ring_multiply / * (pow2_cyc_rings.jl:147-173): primal in, primal out */
 int tfb_ring_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);

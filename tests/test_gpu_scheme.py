@@ -177,7 +177,9 @@ def test_ciphertext_add_sub():
     assert d[0] == 31 and d[5] == 16
     d = T.decrypt(kp, ca - cb)
     assert d[0] == 9 and d[5] == (7 - 9) % 53
-    other = T.BFVParams(R, Rbig, 53)
+    same = T.BFVParams(R, Rbig, 53)      # egal by value, as the reference's `!==` on immutable structs sees it
+    assert T.decrypt(kp, ca + T.CipherText(same, cb.cs))[0] == 31
+    other = T.BFVParams(R, Rbig, 59)     # a different plaintext modulus is a different parameter set
     with pytest.raises(T.UsageError):
         ca + T.CipherText(other, cb.cs)
     with pytest.raises(T.UsageError):

@@ -395,6 +395,14 @@ int tfb_scalar_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* s_residues, ui
     return launch_scalar_mul(c, a, s_residues, out, rows, (cudaStream_t)stream);
 }
 
+int tfb_mul_plain(tfb_ctx* c, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, int accumulate, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(plain); CHECK_PTR(out);
+    if (c->N < 2) { tfb_set_error("mul_plain: N must be at least 2"); return TFB_EINVAL; }
+    return launch_mul_plain(c, a, plain, out, polys, accumulate != 0, (cudaStream_t)stream);
+}
+
 int tfb_ring_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
     if (!rows) return TFB_OK;
@@ -441,8 +449,17 @@ static int ct_tensor_dev(tfb_ctx* c, const u64* c1, const u64* c2, u64* out, u64
     if (rc) return rc;
     u64* A = (u64*)c->stage;
     u64* B = c1 == c2 ? A : A + 2 * batch * poly;   // squaring (c*c, rlwe_she.jl:264-266 with one operand): transform once
-    if ((rc = launch_ntt(c, c1, A, 2 * batch * c->L, false, st))) return rc;
-    if (c1 != c2 && (rc = launch_ntt(c, c2, B, 2 * batch * c->L, false, st))) return rc;
+    if (c1 == c2) {
+        if ((rc = launch_ntt(c, c1, A, 2 * batch * c->L, false, st))) return rc;
+    } else {
+        // both operands in ONE forward launch (rows gathered from the two buffers); two launches where that kernel family does not apply
+        rc = launch_ntt_gather(c, c1, c2, (u32)(2 * batch), c->L, nullptr, A, 4 * batch, st);
+        if (rc == -1) {
+            if ((rc = launch_ntt(c, c1, A, 2 * batch * c->L, false, st))) return rc;
+            rc = launch_ntt(c, c2, B, 2 * batch * c->L, false, st);
+        }
+        if (rc) return rc;
+    }
     if ((rc = launch_tensor_dual(c, A, B, out, batch, st))) return rc;
     return launch_ntt(c, out, out, 3 * batch * c->L, true, st);
 }
@@ -560,6 +577,7 @@ static int joint_ctx(tfb_ctx* cq, tfb_ctx* cb, int K, tfb_ctx** out) {
 }
 
 extern bool g_force_generic;
+extern int g_ntt_version;
 int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(cq); CHECK_CTX(cb);
     if (!batch) return TFB_OK;
@@ -576,15 +594,33 @@ int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const 
         if ((rc = joint_ctx(cq, cb, K, &cj))) return rc;
         const size_t polyj = (size_t)cj->L * cj->N;
         const u64 ch = bfv_chunk(cj, batch);
-        if ((rc = ws_reserve(cj, 7 * ch * polyj * sizeof(u64)))) return rc;
+        const size_t polyk = (size_t)K * cj->N;      // the K new residues of one polynomial
+        // E (4 operand polynomials per pair, dual) | T (3 products per pair) | X (the expansions' new residues only)
+        if ((rc = ws_reserve(cj, (7 * ch * polyj + 4 * ch * polyk) * sizeof(u64)))) return rc;
         u64* E1 = (u64*)cj->ws;
         u64* T = E1 + 4 * ch * polyj;
+        u64* X = T + 3 * ch * polyj;
+        const bool gather = cj->v3_ok && cj->logN >= 12 && cj->logN <= 14 && g_ntt_version == 3 && !g_ntt_force_harvey && g_ntt_max_mode >= 2;
         for (u64 b0 = 0; b0 < batch; b0 += ch) {
             const u64 nb = batch - b0 < ch ? batch - b0 : ch;
             const bool square = c1 == c2;            // c*c: expand and transform the operand once
             u64* E2 = square ? E1 : E1 + 2 * nb * polyj;
-            if ((rc = fast_expand_joint(cq, cb, K, c1 + b0 * 2 * polyq, E1, 2 * nb, st))) return rc;
-            if (!square && (rc = fast_expand_joint(cq, cb, K, c2 + b0 * 2 * polyq, E2, 2 * nb, st))) return rc;
+            const u64* a1 = c1 + b0 * 2 * polyq;
+            const u64* a2 = c2 + b0 * 2 * polyq;
+            if (gather) {
+                // the expansions write only their K new rows; the transform takes the Q rows from the caller's ciphertexts
+                u64* X2 = square ? X : X + 2 * nb * polyk;
+                if ((rc = fast_expand_joint(cq, cb, K, a1, X, 2 * nb, st, false))) return rc;
+                if (!square && (rc = fast_expand_joint(cq, cb, K, a2, X2, 2 * nb, st, false))) return rc;
+                rc = launch_ntt_gather(cj, a1, a2, (u32)(2 * nb), cq->L, X, E1, (square ? 2 : 4) * nb, st);
+                if (rc) return rc == -1 ? (tfb_set_error("internal: gather transform unavailable"), TFB_EINVAL) : rc;
+                if ((rc = launch_tensor_dual(cj, E1, E2, T, nb, st))) return rc;
+                if ((rc = launch_ntt(cj, T, T, 3 * nb * cj->L, true, st))) return rc;
+                if ((rc = fast_contract_joint(cq, cb, K, t, T, out + b0 * 3 * polyq, 3 * nb, st))) return rc;
+                continue;
+            }
+            if ((rc = fast_expand_joint(cq, cb, K, a1, E1, 2 * nb, st))) return rc;
+            if (!square && (rc = fast_expand_joint(cq, cb, K, a2, E2, 2 * nb, st))) return rc;
             if ((rc = launch_ntt(cj, E1, E1, (square ? 2 : 4) * nb * cj->L, false, st))) return rc;   // E1 and E2 are contiguous
             if ((rc = launch_tensor_dual(cj, E1, E2, T, nb, st))) return rc;
             if ((rc = launch_ntt(cj, T, T, 3 * nb * cj->L, true, st))) return rc;

@@ -76,6 +76,7 @@ void tfb_count_launch(int n = 1);
 // rns_kernels.cu
 int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 rows, cudaStream_t st);
 int launch_neg(tfb_ctx* c, const u64* a, u64* out, u64 rows, cudaStream_t st);
+int launch_mul_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 polys, bool accumulate, cudaStream_t st);
 int launch_scalar_mul(tfb_ctx* c, const u64* a, const u64* s_host, u64* out, u64 rows, cudaStream_t st);
 int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 batch, cudaStream_t st);
 int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStream_t st);
@@ -105,7 +106,7 @@ bool fast_base_switch(tfb_ctx* from, tfb_ctx* to, const u64* in, u64* out, u64 p
 bool fast_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st, int* rc);
 // joint-basis BFV multiply (Q u first K primes of the big ring); K = 0: not applicable
 int fast_bfv_joint_k(const tfb_ctx* cq, const tfb_ctx* cb, u64 t);
-int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st, bool copyq = true);   // copyq = false: out [polys][K][N], new residues only
 int fast_contract_joint(tfb_ctx* cq, tfb_ctx* cb, int K, u64 t, const u64* in, u64* out, u64 polys, cudaStream_t st);
 void tfb_forget_ctx_pairs(const tfb_ctx* c);
 int ntt_setup_device();
@@ -116,6 +117,10 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
 int ntt4_setup_device();
 int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
 int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);
+int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStream_t st);   // src: v3k::NttSrc
+// forward transform of `polys` polynomials of c->L rows each: rows [0, lq) of polynomial p from base0 (p < polys0) or base1,
+// rows [lq, c->L) from ext [polys][c->L - lq][N]; out contiguous.  -1: kernel family not applicable.
+int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0, u32 lq, const u64* ext, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
 int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
 int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
 extern bool g_ntt_force_harvey;

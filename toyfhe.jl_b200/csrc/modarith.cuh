@@ -81,26 +81,30 @@ TFB_D u64 shoup_lazy(u64 x, tw_t t, u64 q) { return shoup_lazy(x, t.w, t.wp, q);
 
 // x*w mod q in [0,4q) for primes q = 2^b + e with 32 <= b and e < 2^32 (what the reference's
 // nextprime(2^logq + 1) chains give, crt.jl:282-295); valid for ANY 64-bit x.
-//   quotient: h~ = x1*p1 + hi32(x1*p0) + hi32(x0*p1)  in [h-2, h]  (1 IMAD.WIDE + 2 IMAD.HI instead of the
-//             4 IMAD.WIDE of an exact 64x64 high product; the three products are independent and the
-//             two high words join through one carry chain on the ALU pipe),
+//   quotient: h~ = x1*p1 + floor((x1*p0 + x0*p1) / 2^32)  in [h-1, h]: the two cross products are summed as ONE 64-bit
+//             multiply-accumulate chain whose carry joins the high word (1 IMAD.WIDE + 1 IMAD.HI with addend and carry
+//             out for the cross terms, 1 IMAD.WIDE for x1*p1) -- the round-1 form took the two high halves separately
+//             (2 IMAD.HI) and ptxas re-materialised a {0, t0} register pair per product (1 IMAD.MOV + 1 MOV each);
+//             SASS per butterfly: 28.9 -> 27.1 FMA-heavy cycles, -1.8 % kernel time (tools/ntt_lab.cu, ABL bit 128);
 //   tail:     x*w - h~*q = x*w - h~*e - (h~ << b)  (mod 2^64): one IMAD.WIDE less than a generic q.
 // ne = 2^32 - e, shb = b - 32 (a run-time value: one shift and one 3-input add on the ALU pipe; as a
 // compile-time constant ptxas turns it into a multiply on the FMA-heavy pipe, which bounds the kernels).
 // Measured (IMAD.WIDE/IMAD.HI 4 cycles, IMAD 2 cycles per warp instruction, tools/bfly_bench4.cu).
 TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne, u32 shb) {
 #ifdef __CUDA_ARCH__
-    u32 x0, x1, w0, w1, p0, p1, t0, t1, h0, h1, a, b, lo, hi;
-    u64 t, acc;
+    u32 x0, x1, w0, w1, p0, p1, u0, u1, m1, c, t0, t1, h0, h1, lo, hi;
+    u64 u, t, acc;
     asm("mov.b64 {%0,%1}, %2;" : "=r"(x0), "=r"(x1) : "l"(x));
     asm("mov.b64 {%0,%1}, %2;" : "=r"(w0), "=r"(w1) : "l"(w));
     asm("mov.b64 {%0,%1}, %2;" : "=r"(p0), "=r"(p1) : "l"(wp));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(u) : "r"(x1), "r"(p0));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(u0), "=r"(u1) : "l"(u));
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x1), "r"(p1));
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(a) : "r"(x1), "r"(p0));
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(b) : "r"(x0), "r"(p1));
     asm("mov.b64 {%0,%1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-    asm("{\n\t.reg .u32 s;\n\tadd.cc.u32 s, %2, %3;\n\taddc.u32 %1, %5, 0;\n\tadd.cc.u32 %0, s, %4;\n\taddc.u32 %1, %1, 0;\n\t}"
-        : "=r"(h0), "=&r"(h1) : "r"(t0), "r"(a), "r"(b), "r"(t1));
+    // m1:c = (x0*p1 + u) >> 32 with its carry; h = t + m1 + (c << 32)
+    asm("{\n\t.reg .u32 d;\n\tmad.lo.cc.u32 d, %4, %5, %6;\n\tmadc.hi.cc.u32 %0, %4, %5, %7;\n\taddc.u32 %1, 0, 0;\n\t"
+        "add.cc.u32 %2, %8, %0;\n\taddc.u32 %3, %9, %1;\n\t}"
+        : "=&r"(m1), "=&r"(c), "=&r"(h0), "=&r"(h1) : "r"(x0), "r"(p1), "r"(u0), "r"(u1), "r"(t0), "r"(t1));
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(h0), "r"(ne));
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x0), "r"(w0));
     asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc));
@@ -111,8 +115,10 @@ TFB_D u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 q, u32 ne, u32 shb) {
     asm("mov.b64 %0, {%1,%2};" : "=l"(acc) : "r"(lo), "r"(hi));
     return acc;
 #else
+    // host mirror (tests/emu): the same quotient estimate, so the lazy ranges checked on the CPU are the device's
     const u64 x1 = x >> 32, x0 = x & 0xffffffffu, p1 = wp >> 32, p0 = wp & 0xffffffffu;
-    const u64 h = x1 * p1 + ((x1 * p0) >> 32) + ((x0 * p1) >> 32);
+    const u128 mid = (u128)x1 * p0 + (u128)x0 * p1;
+    const u64 h = x1 * p1 + (u64)(mid >> 32);
     (void)ne; (void)shb;
     return x * w - h * q;
 #endif

@@ -242,8 +242,9 @@ int launch_ntt14p(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, u
     } else {
         ProfScope ps(PC_NTT_FWD, st);
         if (c->v3_ok && !g_ntt_force_harvey && g_ntt_max_mode >= 2) {
-            if (s0 == 0) v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units, 1);
-            else v3k::ntt_fwd_s_kernel<4, false><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units, 1);
+            v3k::NttSrc none = {};
+            if (s0 == 0) v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)units, 1, none);
+            else v3k::ntt_fwd_s_kernel<4, false><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units, 1, none);
         }
         else if (c->ntt_mode >= 1 && !g_ntt_force_harvey && g_ntt_max_mode >= 1)
             ntt_fwd14p_kernel<1><<<grid, Geo::T, ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
@@ -264,7 +265,8 @@ int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_
         const int nsm = c->num_sms > 0 ? c->num_sms : 148;
         const unsigned grid = (unsigned)(rows < (u64)nsm ? rows : (u64)nsm);
         ProfScope ps(PC_NTT_FWD, st);
-        v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, c->L);
+        v3k::NttSrc none = {};
+        v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, c->L, none);
         TFB_CUDA(cudaGetLastError());
         return TFB_OK;
     }
@@ -282,4 +284,23 @@ int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cu
     v3k::ntt_inv_sub_kernel<4><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, s0, (u32)units);
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
+}
+
+// Forward transform of rows gathered from up to three buffers (v3k::NttSrc) into one contiguous output, N = 2^12..2^14 on
+// third-generation primes.  Returns -1 when that kernel family does not apply (the caller copies and transforms).
+int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0, u32 lq, const u64* ext, u64* out, u64 polys, cudaStream_t st) {
+    if (!c->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || g_ntt_version != 3 || c->logN < 12 || c->logN > 14) return -1;
+    v3k::NttSrc src;
+    src.base[0] = base0; src.base[1] = base1; src.ext = ext; src.polys0 = polys0; src.lq = lq; src.lj = c->L;
+    const u64 rows = polys * c->L;
+    if (c->logN == 14) {
+        if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+        const int nsm = c->num_sms > 0 ? c->num_sms : 148;
+        const unsigned grid = (unsigned)(rows < (u64)nsm ? rows : (u64)nsm);
+        ProfScope ps(PC_NTT_FWD, st);
+        v3k::ntt_fwd_s_kernel<4, true><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(nullptr, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, 1, src);
+        TFB_CUDA(cudaGetLastError());
+        return TFB_OK;
+    }
+    return launch_ntt_s_gather(c, &src, out, rows, st);
 }

@@ -23,3 +23,10 @@ int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStrea
     if (c->logN == 13) return v3k::launch_s<3>(c, in, out, polys * c->L, false, st, c->L);
     return -1;
 }
+
+int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStream_t st) {
+    const v3k::NttSrc* s = (const v3k::NttSrc*)src;
+    if (c->logN == 12) return v3k::launch_s<2>(c, nullptr, out, rows, false, st, 1, s);
+    if (c->logN == 13) return v3k::launch_s<3>(c, nullptr, out, rows, false, st, 1, s);
+    return -1;
+}

@@ -38,6 +38,12 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
         : "memory");
 }
 
+// DRAM -> L2 ahead of time: the row a CTA will need NEXT is prefetched while the current one is being transformed, so
+// the bulk copy issued after pass 3's loads finds it in L2 (measured with the quotient change: -5 % kernel time,
+// tools/ntt_lab.cu ABL bits 128 + 2048)
+__device__ __forceinline__ void l2_prefetch(const void* src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // one row of N positions as 32 bulk copies of T words, copy a to its skewed slot
 template <int R>
 __device__ __forceinline__ void tma_load_row_skewed(u64* smem, const u64* src, u64* bar, const u32 lane) {
@@ -65,10 +71,34 @@ __device__ __forceinline__ void build_redtab8(u64* redtab8, const PrimeParams* _
     }
 }
 
+// Where the rows of a forward launch come from when they are not one contiguous buffer: polynomial p = unit / lj of the
+// launch takes its first lq rows from the caller's operand buffers (polynomials [0, polys0) from base[0], the rest from
+// base[1]) and its remaining lj - lq rows from `ext` ([polys][lj - lq][N]).  This is how tfb_ct_tensor transforms c1 and
+// c2 in ONE launch (lq = lj) and how tfb_bfv_mul's joint-basis transform reads the Q rows of the expanded operands
+// straight from the caller's ciphertexts (the expansion then writes only its K new rows, rns_fast.cu).  lj = 0: `in` is
+// one contiguous buffer.
+struct NttSrc {
+    const u64* base[2];
+    const u64* ext;
+    u32 polys0, lq, lj;
+};
+template <int R>
+__device__ __forceinline__ const u64* src_row(const u64* in, const NttSrc& src, const u32 unit, const u32 in_div, const u32 s0, const u64 nrow) {
+    typedef NttGeo<R> Geo;
+    if (src.lj == 0) return in + (u64)((unit / in_div) >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N;
+    const u32 p = unit / src.lj, i = unit - p * src.lj;
+    if (i < src.lq) {
+        const bool second = p >= src.polys0;
+        return src.base[second] + ((u64)(p - (second ? src.polys0 : 0)) * src.lq + i) * Geo::N;
+    }
+    return src.ext + ((u64)p * (src.lj - src.lq) + (i - src.lq)) * Geo::N;
+}
+
 template <int R, bool S0ZERO>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
-                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits, const u32 in_div) {
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits, const u32 in_div,
+                 const NttSrc src) {
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
@@ -85,8 +115,7 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     __syncthreads();
     // in_div > 1 (s0 = 0 only): input row = unit / in_div -- one small-integer polynomial (a keyswitch digit) is
     // transformed under in_div consecutive primes without being replicated in memory first
-    if (t < 32 && unit < nunits)
-        tma_load_row_skewed<R>(smem, in + (u64)((unit / in_div) >> s0) * nrow + (u64)(unit & ((1u << s0) - 1)) * Geo::N, &bar, t);
+    if (t < 32 && unit < nunits) tma_load_row_skewed<R>(smem, src_row<R>(in, src, unit, in_div, s0, nrow), &bar, t);
     u32 parity = 0;
     u64 x[32];
     for (; unit < nunits; unit += gridDim.x) {
@@ -98,6 +127,10 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         // opaque to the optimiser: keeps the per-row address arithmetic inside the loop (hoisted, it
         // is 32 loop-invariant values per thread that ptxas spills to local memory)
         asm volatile("" : "+r"(t));
+        {
+            const u32 nxt = unit + gridDim.x;
+            if (t < 32 && nxt < nunits) l2_prefetch(src_row<R>(in, src, nxt, in_div, s0, nrow) + t * Geo::T, Geo::T * 8);
+        }
         mbar_wait(&bar, parity);
         parity ^= 1;
         v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
@@ -107,8 +140,7 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         v3::pass3_load<R>(x, smem, t);
         __syncthreads();
         const u32 next = unit + gridDim.x;
-        if (t < 32 && next < nunits)
-            tma_load_row_skewed<R>(smem, in + (u64)((next / in_div) >> s0) * nrow + (u64)(next & ((1u << s0) - 1)) * Geo::N, &bar, t);
+        if (t < 32 && next < nunits) tma_load_row_skewed<R>(smem, src_row<R>(in, src, next, in_div, s0, nrow), &bar, t);
         v3::pass3_compute_store<R, S0ZERO>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
     }
 }
@@ -142,6 +174,7 @@ ntt_inv_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         const tw_t* tw = tw_all + (u64)prime * Geo::N;
         v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, nullptr);
         rp.tab8 = redtab8 + prime * 16;
+        if (t < 32 && unit + gridDim.x < nunits) l2_prefetch(in + (u64)(unit + gridDim.x) * Geo::N + t * Geo::T, Geo::T * 8);
         mbar_wait(&bar, parity);
         parity ^= 1;
         v3::inv_pass3_load<R>(x, smem, t);
@@ -216,7 +249,7 @@ int setup_s() {
 }
 // rows of exactly N = 2^(10+R) positions
 template <int R>
-int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st, u32 in_div = 1) {
+int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st, u32 in_div = 1, const NttSrc* src = nullptr) {
     typedef NttGeo<R> Geo;
     if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
     const u64 slots = (u64)(c->num_sms > 0 ? c->num_sms : 148) * (512 / Geo::T);
@@ -226,7 +259,8 @@ int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaSt
         ntt_inv_s_kernel<R><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_inv, c->d_pp, c->L, (u32)rows);
     } else {
         ProfScope ps(PC_NTT_FWD, st);
-        ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, in_div);
+        NttSrc none = {};
+        ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, in_div, src ? *src : none);
     }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;

@@ -354,7 +354,7 @@ __device__ __noinline__ void expand_exact(const u64 (&r)[L], u64* __restrict__ o
 
 template <int L, int K, bool SP>
 __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict__ in, u64* __restrict__ out, const u32 logN,
-                                                           const u64 total, const __grid_constant__ ExpandJTab<L, K> T) {
+                                                           const u64 total, const u32 copyq, const __grid_constant__ ExpandJTab<L, K> T) {
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const u64 p = idx >> logN;
@@ -363,9 +363,11 @@ __global__ void __launch_bounds__(128) expand_joint_kernel(const u64* __restrict
 #pragma unroll
     for (int i = 0; i < L; i++) {
         r[i] = in[((p * L + i) << logN) + n];
-        out[((p * (L + K) + i) << logN) + n] = r[i];
+        if (copyq) out[((p * (L + K) + i) << logN) + n] = r[i];
     }
-    const u64 base = ((p * (L + K) + L) << logN) + n;
+    // copyq = 0: only the K new residues are written, [p][K][N] -- the forward transform reads the Q rows from the
+    // caller's buffer (ntt_v3_kernels.cuh NttSrc), 8 of 17 row writes and their re-reads saved at the headline shape
+    const u64 base = copyq ? ((p * (L + K) + L) << logN) + n : ((p * K) << logN) + n;
     if (!SP) {
         expand_exact<L, K, SP>(r, out, base, logN, T);
         return;
@@ -504,7 +506,7 @@ static bool joint_sp(const tfb_ctx* cq, const tfb_ctx* cb, int K) {
 }
 
 template <int L, int K>
-static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u64 polys, cudaStream_t st) {
+static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u64 polys, cudaStream_t st, bool copyq) {
     typedef ExpandJTab<L, K> Tab;
     static std::map<std::pair<u64, u64>, Tab> cache;
     std::lock_guard<std::mutex> lk(g_fast_mu);
@@ -538,8 +540,8 @@ static int run_expand_joint(tfb_ctx* cq, tfb_ctx* cb, const u64* in, u64* out, u
     const u64 nb = (total + tb - 1) / tb;
     {
         ProfScope ps(PC_BASE_SWITCH, st);
-        if (joint_sp(cq, cb, K)) expand_joint_kernel<L, K, true><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
-        else expand_joint_kernel<L, K, false><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, it->second);
+        if (joint_sp(cq, cb, K)) expand_joint_kernel<L, K, true><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, copyq ? 1u : 0u, it->second);
+        else expand_joint_kernel<L, K, false><<<(unsigned)nb, tb, 0, st>>>(in, out, cq->logN, total, copyq ? 1u : 0u, it->second);
     }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
@@ -609,8 +611,8 @@ int fast_bfv_joint_k(const tfb_ctx* cq, const tfb_ctx* cb, u64 t) {
 #undef JK
     return 0;
 }
-int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st) {
-#define JE(A, B) if ((int)cq->L == A && K == B) return run_expand_joint<A, B>(cq, cb, in, out, polys, st);
+int fast_expand_joint(tfb_ctx* cq, tfb_ctx* cb, int K, const u64* in, u64* out, u64 polys, cudaStream_t st, bool copyq) {
+#define JE(A, B) if ((int)cq->L == A && K == B) return run_expand_joint<A, B>(cq, cb, in, out, polys, st, copyq);
     JOINT_CASES(JE)
 #undef JE
     tfb_set_error("internal: no joint expand kernel");

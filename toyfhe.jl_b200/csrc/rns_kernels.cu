@@ -94,6 +94,36 @@ __global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* 
     }
 }
 
+// Plaintext multiply, broadcast over the batch (ckksencoding.jl:106-111 `a .* c`: every component of every ciphertext
+// times ONE ring element, here in the dual domain; the diagonal-method matmuls of test/ckks_matmul.jl and
+// examples/encrypted_mnist accumulate these products): out[p] (+)= a[p] (.) plain, p < polys, plain [L][N] read once
+// per polynomial from L2.  A plain whose rows are constant is a scalar multiply (ckksencoding.jl:100-103).
+template <bool ACC, bool SP>
+__global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ plain, ulonglong2* __restrict__ out,
+                                 const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total2) {
+    const u64 poly2 = (u64)L << (logN - 1);
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 within = idx % poly2;
+        const PrimeConst pc = pp[within >> (logN - 1)].pc;
+        const ulonglong2 x = a[idx], y = plain[within];
+        ulonglong2 r;
+        if (SP) {
+            const u32 e = (u32)(pc.q - (1ull << 60));
+            r.x = red126_sp60(__umul64hi(x.x, y.x), x.x * y.x, pc.q, e);
+            r.y = red126_sp60(__umul64hi(x.y, y.y), x.y * y.y, pc.q, e);
+        } else {
+            r.x = barrett_mul(x.x, y.x, pc);
+            r.y = barrett_mul(x.y, y.y, pc);
+        }
+        if (ACC) {
+            const ulonglong2 o = out[idx];
+            r.x = add_mod(r.x, o.x, pc.q);
+            r.y = add_mod(r.y, o.y, pc.q);
+        }
+        out[idx] = r;
+    }
+}
+
 static inline unsigned grid_for(u64 work, unsigned tb) {
     u64 nb = (work + tb - 1) / tb;
     const u64 cap = 148ull * 16;
@@ -108,6 +138,20 @@ int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 r
     else if (op == 1) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<1><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
     else if (c->ntt_mode == 2 && !g_force_generic) { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<3><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
     else { ProfScope ps(PC_ELEMENTWISE, st); binop_kernel<2><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)b, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_mul_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 polys, bool accumulate, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    const u64 total2 = polys * c->L * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    const bool sp = c->ntt_mode == 2 && !g_force_generic;
+    ProfScope ps(PC_ELEMENTWISE, st);
+#define MP(A, S) mul_plain_kernel<A, S><<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)plain, (ulonglong2*)out, c->d_pp, c->L, c->logN, total2)
+    if (accumulate) { if (sp) MP(true, true); else MP(true, false); }
+    else { if (sp) MP(false, true); else MP(false, false); }
+#undef MP
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

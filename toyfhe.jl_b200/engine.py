@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
-    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul",
+    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
     "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
@@ -227,6 +227,14 @@ class Context:
         out = self.empty(a.shape) if out is None else out
         sr = (C.c_uint64 * self.L)(*[int(s) % q for q in self.qs])
         _check(self._lib.tfb_scalar_mul(self.h, _ptr(a), sr, _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
+        return out
+
+    def mul_plain(self, a, plain, out=None, accumulate=False, stream=None):
+        """out[p] (+)= a[p] (.) plain over every polynomial p of ``a`` (plain: one [L][N] element, same domain)"""
+        assert plain.numel() == self.N * self.L
+        out = self.empty(a.shape) if out is None else out
+        _check(self._lib.tfb_mul_plain(self.h, _ptr(a), _ptr(plain), _ptr(out), C.c_uint64(self._polys(a)), C.c_int(1 if accumulate else 0),
+                                       _stream_ptr(stream, self.device)))
         return out
 
     def galois(self, a, g: int, out=None, stream=None):
