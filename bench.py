@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2] / configs[4] workload pipelines")
+    ap.add_argument("--mnist-batch", type=int, default=16, help="encrypted-MNIST pipelines per GPU (BASELINE configs[4]; 512 per GPU = 4096 on 8 GPUs)")
+    ap.add_argument("--matmul-batch", type=int, default=8, help="CKKS 128x128 matmul ciphertexts per GPU (BASELINE configs[2])")
     return ap.parse_args()
 
 
@@ -292,6 +295,34 @@ def run_ours(args):
     e2e_s = float(te.item())
     e2e_value = world * Be / e2e_s
 
+    # ---- BASELINE configs[2] and configs[4] as checked device-resident pipelines (workloads/): every rank runs its own
+    # batch of independent pipelines (ciphertext-parallel, no data-path collective); rate = all ranks' pipelines / max time
+    configs = None
+    if not args.no_configs:
+        from workloads import ckks_matmul as W3, mnist as W5
+        configs = {}
+        r3 = W3.run(args.matmul_batch, 128, 2 ** 15, 9, reps=2)
+        r5 = W5.run(args.mnist_batch, 64, 2 ** 13, reps=1)
+        tt = torch.tensor([r3["ms_per_batch"], r5["ms_per_batch"], r3["max_abs_err"], r5["max_abs_err"],
+                           r3["last_of_batch_max_abs_err"], r5["last_of_batch_max_abs_err"]], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        m3, m5, e3, e5, l3, l5 = [float(v) for v in tt.tolist()]
+        configs["c3_ckks_matmul"] = {
+            "workload": "CKKS N=2^15, chain 60+9x40+special 60 (11 primes), ModulusRaised CRT-digit keyswitch, 128x128 diagonal matmul: "
+                        "127 rotations + 128 plaintext-vector multiplies + 1 rescale per ciphertext (test/ckks_matmul.jl:30-44 scaled up)",
+            "batch_per_gpu": args.matmul_batch, "ms_per_batch": m3, "matmuls_per_s": world * args.matmul_batch / (m3 * 1e-3),
+            "rotations_per_s": world * args.matmul_batch * 127 / (m3 * 1e-3), "max_abs_err_vs_float64": max(e3, l3), "atol": 1e-5,
+            "correct": max(e3, l3) < 1e-5, "kernel_launches_per_batch": r3["kernel_launches_per_batch"]}
+        configs["c5_encrypted_mnist"] = {
+            "workload": "encrypted-MNIST CKKS inference (examples/encrypted_mnist/infer.jl:96-177): N=2^13, primes 60+5x40+special 60, per pipeline "
+                        "(64 images) 196 ct*scalar, 5 ct*ct + relinearisations, 10 rescales, 315 rotations, 320 plaintext-vector multiplies; "
+                        "synthetic weights and images of the model's shapes",
+            "batch_per_gpu": args.mnist_batch, "ms_per_batch": m5, "pipelines_per_s": world * args.mnist_batch / (m5 * 1e-3),
+            "images_per_s": world * args.mnist_batch * 64 / (m5 * 1e-3), "max_abs_err_vs_float64": max(e5, l5),
+            "labels_agree": bool(r5["labels_agree"]), "correct": max(e5, l5) < 1e-3 and bool(r5["labels_agree"]),
+            "kernel_launches_per_batch": r5["kernel_launches_per_batch"]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,6 +393,7 @@ def run_ours(args):
                     "achieved_gbs": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "frac_of_peak": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / peak,
                     "algorithmic_bytes_per_launch": ntt_bytes},
         "cpu_baseline": cpu,
+        "configs": configs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

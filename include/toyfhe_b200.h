@@ -14,7 +14,13 @@
  *   - all buffer arguments are DEVICE pointers, except in the *_host entry points,
  *     which take HOST pointers and do the host<->device copies themselves
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
- *     asynchronous on that stream; calls on one ctx must be serialised by the caller
+ *     asynchronous on that stream.  HOST side: calls on one ctx must not overlap in time (one host thread
+ *     at a time per ctx).  DEVICE side: a ctx owns scratch buffers that its composite operations share;
+ *     consecutive calls on the same stream are ordered by the stream, and calls on DIFFERENT streams are
+ *     ordered by the library (the later call's stream waits on an event recorded on the earlier call's
+ *     stream), so issuing work on one ctx from several streams is safe but does not overlap.
+ *     Distinct contexts (and devices) are independent.  Every entry point runs with ctx's device current
+ *     and restores the caller's device before returning
  *   - in-place (out == in) is allowed unless stated otherwise
  *   - every function returns 0 on success or a TFB_E* code; the message is
  *     available from tfb_last_error() (thread-local).  Nothing throws or aborts

@@ -29,6 +29,27 @@ struct DeviceGuard {
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
+// Calls that use a context's scratch (ws / stage / io, cached joint contexts) on DIFFERENT streams are ordered on the device:
+// when a call arrives on another stream than the previous one, an event is recorded on the PREVIOUS stream (it covers
+// everything submitted there so far, in particular the previous call's last kernel) and the new stream waits on it.
+// Calls that stay on one stream -- the normal case -- cost nothing: stream order already serialises them.
+struct ScratchGuard {
+    tfb_ctx* c;
+    cudaStream_t st;
+    ScratchGuard(tfb_ctx* c_, void* stream) : c(c_), st((cudaStream_t)stream) {
+        if (c->scratch_used && c->scratch_stream != st) {
+            if (!c->scratch_done) cudaEventCreateWithFlags(&c->scratch_done, cudaEventDisableTiming);
+            if (c->scratch_done && cudaEventRecord(c->scratch_done, c->scratch_stream) == cudaSuccess) cudaStreamWaitEvent(st, c->scratch_done, 0);
+            else cudaGetLastError();   // the previous stream no longer exists: its work has completed or been abandoned by the caller
+        }
+    }
+    ~ScratchGuard() {
+        c->scratch_stream = st;
+        c->scratch_used = true;
+    }
+    ScratchGuard(const ScratchGuard&) = delete;
+    ScratchGuard& operator=(const ScratchGuard&) = delete;
+};
 #define TFB_CAT2(a, b) a##b
 #define TFB_CAT(a, b) TFB_CAT2(a, b)
 #define CHECK_CTX(c)                                                \
@@ -246,6 +267,9 @@ int tfb_ctx_create(int device, uint32_t N, uint32_t L, const uint64_t* q, const 
     c->d_halfmr = nullptr;
     c->ws = c->stage = c->io = nullptr;
     c->d_ckks_pos = nullptr;
+    c->scratch_done = nullptr;
+    c->scratch_stream = nullptr;
+    c->scratch_used = false;
     c->ws_bytes = c->stage_bytes = c->io_bytes = 0;
     c->conv_ok = false;
     c->num_sms = 0;
@@ -318,6 +342,7 @@ int tfb_ctx_destroy(tfb_ctx* c) {
     cudaFree(c->stage);
     cudaFree(c->io);
     cudaFree(c->d_ckks_pos);
+    if (c->scratch_done) cudaEventDestroy(c->scratch_done);
     delete c;
     return TFB_OK;
 }
@@ -362,12 +387,14 @@ int tfb_sync(tfb_ctx* c, void* stream) {
 // ------------------------------------------------------------------ transforms
 int tfb_ntt_fwd(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!rows) return TFB_OK;
     CHECK_PTR(in); CHECK_PTR(out);
     return launch_ntt(c, in, out, rows, false, (cudaStream_t)stream);
 }
 int tfb_ntt_inv(tfb_ctx* c, const uint64_t* in, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!rows) return TFB_OK;
     CHECK_PTR(in); CHECK_PTR(out);
     return launch_ntt(c, in, out, rows, true, (cudaStream_t)stream);
@@ -405,6 +432,7 @@ int tfb_mul_plain(tfb_ctx* c, const uint64_t* a, const uint64_t* plain, uint64_t
 
 int tfb_ring_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!rows) return TFB_OK;
     CHECK_PTR(a); CHECK_PTR(b); CHECK_PTR(out);
     cudaStream_t st = (cudaStream_t)stream;
@@ -466,6 +494,7 @@ static int ct_tensor_dev(tfb_ctx* c, const u64* c1, const u64* c2, u64* out, u64
 
 int tfb_ct_tensor(tfb_ctx* c, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(c);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!batch) return TFB_OK;
     CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
     return ct_tensor_dev(c, c1, c2, out, batch, (cudaStream_t)stream);
@@ -481,6 +510,7 @@ int tfb_bfv_switch(tfb_ctx* from, tfb_ctx* to, const uint64_t* in, uint64_t* out
 int tfb_bfv_contract(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* in, uint64_t* out, uint64_t polys, void* stream) {
     CHECK_CTX(cq); CHECK_CTX(cb);
     if (!polys) return TFB_OK;
+    if (t == 0) { tfb_set_error("bfv_contract: plaintext modulus is zero"); return TFB_EINVAL; }
     CHECK_PTR(in); CHECK_PTR(out);
     if (in == out) { tfb_set_error("tfb_bfv_contract cannot run in place"); return TFB_EINVAL; }
     return launch_bfv_contract(cq, cb, t, in, out, polys, (cudaStream_t)stream);
@@ -507,12 +537,14 @@ int tfb_centered_mod(tfb_ctx* c, uint64_t t, const uint64_t* b, uint64_t* out, u
 }
 int tfb_ckks_encode(tfb_ctx* c, double scale, const double* slots, uint64_t* out, uint64_t polys, void* stream) {
     CHECK_CTX(c);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!polys) return TFB_OK;
     CHECK_PTR(slots); CHECK_PTR(out);
     return launch_ckks_encode(c, scale, slots, out, polys, (cudaStream_t)stream);
 }
 int tfb_ckks_decode(tfb_ctx* c, double scale, const uint64_t* in, double* slots, uint64_t polys, void* stream) {
     CHECK_CTX(c);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
     if (!polys) return TFB_OK;
     CHECK_PTR(in); CHECK_PTR(slots);
     return launch_ckks_decode(c, scale, in, slots, polys, (cudaStream_t)stream);
@@ -580,6 +612,8 @@ extern bool g_force_generic;
 extern int g_ntt_version;
 int tfb_bfv_mul(tfb_ctx* cq, tfb_ctx* cb, uint64_t t, const uint64_t* c1, const uint64_t* c2, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(cq); CHECK_CTX(cb);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(cq, stream);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(cb, stream);
     if (!batch) return TFB_OK;
     CHECK_PTR(c1); CHECK_PTR(c2); CHECK_PTR(out);
     if (cq->N != cb->N) { tfb_set_error("bfv_mul: ring degrees differ"); return TFB_EINVAL; }
@@ -687,6 +721,8 @@ static int ks_digits_dual(tfb_ctx* c, tfb_ctx* r, uint32_t w, const u64* cend, u
 int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
                   uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(c);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(ext ? ext : c, stream);
     if (!batch) return TFB_OK;
     CHECK_PTR(key_dual); CHECK_PTR(ct); CHECK_PTR(out);
     if (comps != 2 && comps != 3) { tfb_set_error("keyswitch: ciphertext must have 2 or 3 components"); return TFB_EINVAL; }
@@ -726,6 +762,8 @@ int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual
 int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
                         uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
     CHECK_CTX(c); CHECK_CTX(r);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(r, stream);
     if (!batch) return TFB_OK;
     CHECK_PTR(key_dual); CHECK_PTR(ct); CHECK_PTR(out);
     if (comps != 2 && comps != 3) { tfb_set_error("keyswitch: ciphertext must have 2 or 3 components"); return TFB_EINVAL; }

@@ -39,6 +39,11 @@ struct tfb_ctx {
     size_t stage_bytes;
     void* io;
     size_t io_bytes;
+    // the scratch above is shared by every asynchronous call on this context: `scratch_done` is recorded on the stream of
+    // the last call that used it and the next call's stream waits on it when it is a different stream (api.cu ScratchGuard)
+    cudaEvent_t scratch_done;
+    cudaStream_t scratch_stream;
+    bool scratch_used;
     unsigned* d_ckks_pos;   // [N/2] slot positions (3^(i+1) mod 2N) >> 1 of the CKKS encoding (ckks_kernels.cu), built on first use
 };
 

@@ -82,6 +82,9 @@ struct NttSrc {
     const u64* ext;
     u32 polys0, lq, lj;
 };
+// Evaluated only while no residues are live (before the first row and at the top of the row loop): the next row's address
+// then waits in shared memory until the bulk copy is issued after pass 3's loads, so the gather costs the butterfly
+// ladder no registers (computed at the copy's issue point it cost 40-64 bytes of spill stack, ptxas -v).
 template <int R>
 __device__ __forceinline__ const u64* src_row(const u64* in, const NttSrc& src, const u32 unit, const u32 in_div, const u32 s0, const u64 nrow) {
     typedef NttGeo<R> Geo;
@@ -102,6 +105,7 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
+    __shared__ const u64* next_src;
     __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
     const u32 s0 = S0ZERO ? 0 : s0_;
     u32 t = threadIdx.x;
@@ -129,7 +133,11 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         asm volatile("" : "+r"(t));
         {
             const u32 nxt = unit + gridDim.x;
-            if (t < 32 && nxt < nunits) l2_prefetch(src_row<R>(in, src, nxt, in_div, s0, nrow) + t * Geo::T, Geo::T * 8);
+            if (t < 32 && nxt < nunits) {
+                const u64* p = src_row<R>(in, src, nxt, in_div, s0, nrow);
+                l2_prefetch(p + t * Geo::T, Geo::T * 8);
+                if (t == 0) next_src = p;       // read back after pass 3's loads (three barriers later)
+            }
         }
         mbar_wait(&bar, parity);
         parity ^= 1;
@@ -140,7 +148,7 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         v3::pass3_load<R>(x, smem, t);
         __syncthreads();
         const u32 next = unit + gridDim.x;
-        if (t < 32 && next < nunits) tma_load_row_skewed<R>(smem, src_row<R>(in, src, next, in_div, s0, nrow), &bar, t);
+        if (t < 32 && next < nunits) tma_load_row_skewed<R>(smem, next_src, &bar, t);
         v3::pass3_compute_store<R, S0ZERO>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
     }
 }

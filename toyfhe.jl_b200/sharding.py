@@ -124,14 +124,33 @@ def key_rows_for_shard(key_dual: torch.Tensor, lo: int, hi: int) -> torch.Tensor
     return key_dual[:, :, lo:hi, :].contiguous()
 
 
+_GATHER_BUF = {}
+
+
 def allgather_prime_rows(local: torch.Tensor, L: int, group=None) -> torch.Tensor:
-    """local [..., Ls, N] (this rank's prime rows, ragged over ranks) -> [..., L, N] on every rank."""
+    """local [..., Ls, N] (this rank's prime rows, ragged over ranks) -> [..., L, N] on every rank.
+    Equal shard sizes (L divisible by the world size: 8 primes on 2/4/8 GPUs): ONE all_gather_into_tensor into a cached
+    [world][...] buffer and one strided copy into the [..., L, N] result -- no padding, no per-rank tensors, no cat."""
     rank, world = _world(group)
     if world == 1:
         return local
     sizes = shard_sizes(L, world)
-    mx = max(sizes)
     lead, N = tuple(local.shape[:-2]), local.shape[-1]
+    if len(set(sizes)) == 1 and hasattr(dist, "all_gather_into_tensor"):
+        Ls = sizes[0]
+        key = (world, lead, Ls, N, local.dtype, str(local.device))
+        buf = _GATHER_BUF.get(key)
+        if buf is None:
+            buf = _GATHER_BUF[key] = torch.empty((world,) + lead + (Ls, N), dtype=local.dtype, device=local.device)
+        try:
+            dist.all_gather_into_tensor(buf, local.contiguous(), group=group)
+            out = torch.empty(lead + (L, N), dtype=local.dtype, device=local.device)
+            # out[..., r*Ls + i, :] = buf[r, ..., i, :]
+            out.view(lead + (world, Ls, N)).copy_(buf.movedim(0, len(lead)))
+            return out
+        except (RuntimeError, NotImplementedError):
+            pass                                        # backend without the fused collective: the general path below
+    mx = max(sizes)
     pad = torch.zeros(lead + (mx, N), dtype=local.dtype, device=local.device)
     pad[..., : local.shape[-2], :] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
