@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2] / configs[4] workload pipelines")
-    ap.add_argument("--mnist-batch", type=int, default=16, help="encrypted-MNIST pipelines per GPU (BASELINE configs[4]; 512 per GPU = 4096 on 8 GPUs)")
-    ap.add_argument("--matmul-batch", type=int, default=8, help="CKKS 128x128 matmul ciphertexts per GPU (BASELINE configs[2])")
+    ap.add_argument("--mnist-batch", type=int, default=64, help="encrypted-MNIST pipelines per GPU (BASELINE configs[4]; 512 per GPU = 4096 on 8 GPUs)")
+    ap.add_argument("--matmul-batch", type=int, default=16, help="CKKS 128x128 matmul ciphertexts per GPU (BASELINE configs[2])")
     return ap.parse_args()
 
 
@@ -188,6 +188,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # each rank keeps to its own slice of the host cores, set BEFORE its pinned buffers are allocated and first touched
+        # (tools/host_link_probe.py: on this pool's single-socket VM hosts it changes nothing, on a multi-socket host it
+        # keeps a rank's staging memory next to the cores that drive its copies)
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        os.sched_setaffinity(0, cores[local * per:(local + 1) * per] or cores)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") on fd 1 when the first
         # communicator is created, so fd 1 points at stderr until that has happened
@@ -353,19 +360,19 @@ def run_ours(args):
         a = kernels[dom]["achieved_gbs"]
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of this kernel from the committed ncu capture (same shape), scaled to this batch
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if dom in tr:
                 traffic = float(tr[dom]) * B / float(tr["batch"])
-                traffic_src = "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+                traffic_src = "profiles/r02_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
         except Exception:
             pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
                     "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg[dom] // max(1, kernels[dom]["launches"] // K),
                     "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
-                    "note": "integer work on 61-bit residues: the FMA-heavy (IMAD) pipe is 67% busy in the transforms and 86% in the "
+                    "note": "integer work on 61-bit residues: the FMA-heavy (IMAD) pipe is 66% busy in the transforms and 87% in the "
                             "base conversions at these rates and bounds them before HBM does (DESIGN.md section 5, "
-                            "profiles/r01f_ncu_bfv_step.txt)"}
+                            "profiles/r02_ncu_bfv_step.txt, profiles/r02_ntt_ablation.txt)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -384,8 +391,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * 2 * L_Q * Nb),
                 "d2h_bytes_per_step": int(Be * 3 * L_Q * Nb), "batch": Be, "ms_per_step": e2e_s * 1e3,
                 "api": "tfb_bfv_mul_host (pinned host buffers; H2D, kernels and D2H pipelined over 8-pair chunks on three streams)",
-                "bound": "PCIe Gen5 x16: 43.9 GB/s per direction with both directions busy (tools/pcie_probe.py, profiles/r01_pcie.txt); "
-                         "4 MiB in + 3 MiB out per pair => ~11.0k pairs/s per GPU link"},
+                "bound": "host link: 48 GB/s per direction with both directions busy on one GPU, 39.6 GB/s per rank on two (aggregate H2D+D2H "
+                         "stops growing with the number of ranks on this pool's single-socket VM hosts: tools/host_link_probe.py, "
+                         "profiles/r02_host_link.txt); 4 MiB in + 3 MiB out per pair => ~11.5k pairs/s for one GPU's link"},
         "roofline": roofline,
         "kernels": kernels,
         "ntt_fwd": {"value": world * ntt_polys / (ntt_ms * 1e-3), "unit": "RNS-NTT/s (N=2^14, L=8)",

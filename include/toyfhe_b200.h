@@ -68,6 +68,9 @@ int tfb_debug_force_generic(int on);
 /* kernel selection hook (testing): 1 = one CTA per row (512 threads x 32 residues, ntt_core.cuh),
  * 3 (default) = persistent TMA-prefetched third-generation kernels; both must agree bit for bit */
 int tfb_debug_ntt_version(int v);
+/* testing hook for N = 2^15 / 2^16, forward, out of place: 1 (default) = the row's last global level is applied while the
+ * sub-block kernel loads its operands (one HBM pass less), 0 = every global level as its own pass; must agree bit for bit */
+int tfb_debug_ntt_cross(int on);
 /* testing hook: force the Harvey (conditional subtract per level) forward ladder even when every prime
  * qualifies for the lazy ladder */
 int tfb_debug_ntt_force_harvey(int on);

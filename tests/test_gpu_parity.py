@@ -588,6 +588,31 @@ def test_ntt_kernel_variants(version, mode, logN, logqs):
         T.ntt_max_mode(2)
 
 
+@pytest.mark.parametrize("logN,logqs,B", [(15, [60, 40, 40], 60), (16, [60], 80), (15, [50], 3), (15, [60] + [40] * 9 + [60], 30)])
+def test_ntt_long_rows_last_global_level_on_load(logN, logqs, B):
+    """rows of 2^15 / 2^16, forward, out of place: the last global level applied while the sub-block kernel loads (default)
+    against every level as its own pass and against the oracle; in place falls back to the separate passes"""
+    N = 1 << logN
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(logN + len(logqs))
+    a = _rand(rng, N, qs, (B,))
+    a[0, 0, :] = qs[0] - 1
+    want = orc.nntt(a[:4])
+    d = ctx.to_device(a)
+    f = ctx.ntt_fwd(d)
+    assert np.array_equal(H(f[:4]), want)
+    T.ntt_cross(False)
+    try:
+        g = ctx.ntt_fwd(d)
+    finally:
+        T.ntt_cross(True)
+    assert bool((f == g).all())
+    f2 = d.clone()
+    ctx.ntt_fwd(f2, out=f2)
+    assert bool((f2 == f).all())
+    assert np.array_equal(H(ctx.ntt_inv(f)), a)
+
+
 def test_many_primes_and_conversion_limits():
     """contexts hold up to 64 primes (transforms and element-wise work are per prime); the exact base conversions stop at
     32 primes and say so instead of computing something else"""

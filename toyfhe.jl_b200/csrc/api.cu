@@ -159,6 +159,11 @@ int tfb_debug_ntt_max_mode(int m) {
     g_ntt_max_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
     return TFB_OK;
 }
+int tfb_debug_ntt_cross(int on) {
+    extern bool g_ntt_cross;
+    g_ntt_cross = on != 0;
+    return TFB_OK;
+}
 int tfb_debug_ntt_force_harvey(int on) {
     extern bool g_ntt_force_harvey;
     g_ntt_force_harvey = on != 0;

@@ -128,6 +128,7 @@ int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStr
 int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0, u32 lq, const u64* ext, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
 int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu
 int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
+int launch_ntt_fwd_cross(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
 extern bool g_ntt_force_harvey;
 extern int g_ntt_max_mode;  // debug cap on the ladder mode (2 = no cap)
 extern int g_ntt_version;  // 1 = one CTA per row (ntt_core.cuh), 3 = persistent third-generation kernels (default)

@@ -224,6 +224,37 @@ TFB_HD void pass3_compute_store(u64* x, u64* __restrict__ orow, const tw_t* __re
     }
 }
 
+// ------------------------------------------------------------------ rows of 2^(14+s0) positions, s0 >= 1: last global level on load
+// Global level s0 pairs position p of sub-block 2m (X) with position p of sub-block 2m+1 (Y), twiddle index
+// 2^(s0-1) + m.  The CTA that owns sub-block blk = 2m + rank reads BOTH (canonical) operands straight from global memory
+// and forms X' = X + wY (rank 0) or Y' = X - wY + 4q (rank 1) itself: one extra Shoup product per position instead of a
+// separate read-modify-write pass over the row in HBM.  Results are below 5q; the five levels of pass 1 then reduce at
+// level 3 (bound 5 -> 9 -> 13 -> (reduce) 6 -> 10 -> 14; pass 2 reduces at its level 1).
+template <int R>
+TFB_HD void pass1_cross_global(u64* x, const u64* __restrict__ even, const u64* __restrict__ odd, const u32 rank, const tw_t wc,
+                               const Red3& rp, const u32 t) {
+#pragma unroll
+    for (int a = 0; a < 32; a++) {
+        const u64 X = even[a * NttGeo<R>::T + t], Y = odd[a * NttGeo<R>::T + t];
+        const u64 tt = shoup_lazy4(Y, wc.w, wc.wp, rp.q, rp.ne, rp.shb);
+#ifndef __CUDA_ARCH__
+        if (tt >= rp.q4 || X >= rp.q) g_emu_overflow3++;
+#endif
+        x[a] = rank ? X - tt + rp.q4 : X + tt;
+    }
+}
+TFB_HD void pass1_cross_levels(u64* x, const tw_t* __restrict__ tw, const Red3& rp, const u32 s0, const u32 blk) {
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
+    levels3<5, 0x04>(x, tw, tb, rp);
+}
+template <int R>
+TFB_HD void pass1_store(const u64* x, u64* smem, const u32 t) {
+#pragma unroll
+    for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
+}
+
 // ------------------------------------------------------------------ inverse (pow2_cyc_rings.jl:308-318)
 // GS butterfly  X' = X + Y, Y' = (X - Y) w.  Products come back in [0,4q) (shoup_lazy4), so every level after the
 // first brings the sum back with the same table: k is estimated from the high words only (it can be one short of

@@ -19,6 +19,7 @@ int g_ntt_version = 3;  // 1 = one CTA per row (512x32, ntt_core.cuh), 3 = persi
                         // cluster-pair kernels of round 1 were measured slower and removed (profiles/r01_ntt_sizes*.txt keep their numbers)
 bool g_ntt_force_harvey = false;
 int g_ntt_max_mode = 2;
+bool g_ntt_cross = true;   // N > 2^14 forward, out of place: last global level applied on load (testing hook tfb_debug_ntt_cross)
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long tfb_launch_count() { return g_launches.load(); }
 void tfb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
@@ -238,6 +239,22 @@ int launch_ntt(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cuda
     const unsigned tb = 256;
     const unsigned nb = (unsigned)((total / 2 + tb - 1) / tb);   // two butterflies per thread
     if (!inverse) {
+        if (g_ntt_version == 3 && in != out && g_ntt_cross) {
+            // levels 1..s0-1 as global passes, level s0 inside the sub-block kernel's loads (one HBM pass less)
+            const u64* src = in;
+            for (u32 s = 1; s + 1 <= s0; s++) {
+                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }
+                src = tmp;
+            }
+            TFB_CUDA(cudaGetLastError());
+            rc = launch_ntt_fwd_cross(c, src, out, rows, s0, st);
+            if (rc != -1) return rc;
+            if (s0 > 1) {   // not applicable after all: finish the remaining global level, then the plain sub-blocks
+                { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(tmp, tmp, c->d_fwd, c->d_pp, c->L, logN, s0, total); }
+                TFB_CUDA(cudaGetLastError());
+                return launch_ntt14p(c, tmp, out, rows, false, s0, st);
+            }
+        }
         const u64* src = in;
         for (u32 s = 1; s <= s0; s++) {
             { ProfScope ps(PC_NTT_OTHER, st); ntt_fwd_stage_kernel<<<nb, tb, 0, st>>>(src, tmp, c->d_fwd, c->d_pp, c->L, logN, s, total); }

@@ -217,6 +217,7 @@ int ntt3_setup_device() {
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd14p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_s_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv14p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
+    TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_inv_sub_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     int rc = v3k::setup_s<4>();
     if (rc) return rc;
@@ -303,4 +304,18 @@ int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0
         return TFB_OK;
     }
     return launch_ntt_s_gather(c, &src, out, rows, st);
+}
+
+// forward sub-blocks of rows of 2^(14+s0) positions with the last global level applied on load (`in` carries levels
+// 1..s0-1); out of place only.  -1: not applicable (the caller runs that level as a global pass).
+int launch_ntt_fwd_cross(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st) {
+    if (!c->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || s0 < 1 || in == out) return -1;
+    const u64 units = rows << s0;
+    if (units > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+    const u64 nsm = (u64)(c->num_sms > 0 ? c->num_sms : 148);
+    const unsigned grid = (unsigned)(units < nsm ? units : nsm);
+    ProfScope ps(PC_NTT_FWD, st);
+    v3k::ntt_fwd_x_kernel<4><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, s0, (u32)units);
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
 }

@@ -153,6 +153,48 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
     }
 }
 
+// Forward sub-blocks of rows of 2^(10+R+s0) positions, s0 >= 1, with the row's LAST global level applied while loading
+// (v3::pass1_cross_global): `in` carries levels 1..s0-1 (canonical; s0 = 1: the untouched input row).  Both CTAs of a
+// pair read both sub-blocks (the second read is an L2 hit), so the separate HBM pass of that level -- 27 % of the
+// N = 2^15 forward transform -- disappears at the price of one more product per position.  OUT OF PLACE only: a CTA
+// writes natural-order outputs all over the row while its partner may still be reading the inputs.
+template <int R>
+__global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
+ntt_fwd_x_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0, const u32 nunits) {
+    typedef NttGeo<R> Geo;
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
+    u32 t = threadIdx.x;
+    const u64 nrow = (u64)Geo::N << s0;
+    build_redtab(redtab, pp, L, t, Geo::T);
+    __syncthreads();
+    u64 x[32];
+    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const u64 row = unit >> s0;
+        const u32 blk = unit & ((1u << s0) - 1);
+        const u32 prime = (u32)(row % L);
+        const tw_t* tw = tw_all + (u64)prime * nrow;
+        const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
+        asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
+        const u64* even = in + row * nrow + (u64)(blk & ~1u) * Geo::N;
+        {   // the pair this CTA handles next: DRAM -> L2 while this one is transformed
+            const u32 nxt = unit + gridDim.x;
+            if (t < 64 && nxt < nunits)
+                l2_prefetch(in + (u64)(nxt >> s0) * nrow + (u64)((nxt & ((1u << s0) - 1)) & ~1u) * Geo::N + (u64)t * Geo::T, Geo::T * 8);
+        }
+        v3::pass1_cross_global<R>(x, even, even + Geo::N, blk & 1, tw[(1u << (s0 - 1)) + (blk >> 1)], rp, t);
+        v3::pass1_cross_levels(x, tw, rp, s0, blk);
+        v3::pass1_store<R>(x, smem, t);
+        __syncthreads();
+        v3::pass2<R>(x, smem, tw, rp, t, s0, blk);
+        __syncthreads();
+        v3::pass3_load<R>(x, smem, t);
+        __syncthreads();              // the buffer is free for the next unit's pass 1
+        v3::pass3_compute_store<R, false>(x, out + row * nrow, tw_all + (u64)(L + prime) * nrow, rp, t, s0, blk);
+    }
+}
+
 // inverse, s0 == 0 only (for longer rows the natural-order input of a sub-block is strided)
 template <int R>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)

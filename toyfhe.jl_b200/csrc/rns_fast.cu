@@ -431,7 +431,11 @@ __global__ void __launch_bounds__(128) contract_joint_kernel(const u64* __restri
 #pragma unroll
     for (int i = 0; i < L; i++) acc[i] = 0;
     u64 F = 1ull << 57;
-#pragma unroll 1
+#ifndef TFB_CONTRACT_UNROLL
+#define TFB_CONTRACT_UNROLL 1
+#endif
+    constexpr int kUnroll = TFB_CONTRACT_UNROLL;
+#pragma unroll kUnroll
     for (int j = 0; j < K; j++) {
         const PrimeConst pc = T.pcb[j];
         const u64 xj = in[((p * (L + K) + L + j) << logN) + n];

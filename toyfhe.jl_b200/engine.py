@@ -22,7 +22,7 @@ _lib = None
 ABI_SYMBOLS = [
     "tfb_last_error", "tfb_version", "tfb_kernel_launches",
     "tfb_profile_enable", "tfb_profile_classes", "tfb_profile_class_name", "tfb_profile_read",
-    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode",
+    "tfb_debug_force_generic", "tfb_debug_ntt_version", "tfb_debug_ntt_force_harvey", "tfb_debug_ntt_max_mode", "tfb_debug_ntt_cross",
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
@@ -79,6 +79,11 @@ def ntt_version(v: int) -> None:
 def ntt_force_harvey(on: bool) -> None:
     """testing hook: disable the lazy forward ladder"""
     _check(load_library().tfb_debug_ntt_force_harvey(C.c_int(1 if on else 0)))
+
+
+def ntt_cross(on: bool) -> None:
+    """testing hook: N > 2^14 forward out of place with (default) or without the last global level applied on load"""
+    _check(load_library().tfb_debug_ntt_cross(C.c_int(1 if on else 0)))
 
 
 def ntt_max_mode(m: int) -> None:
