@@ -330,6 +330,46 @@ def run_ours(args):
             "labels_agree": bool(r5["labels_agree"]), "correct": max(e5, l5) < 1e-3 and bool(r5["labels_agree"]),
             "kernel_launches_per_batch": r5["kernel_launches_per_batch"]}
 
+        # BASELINE configs[3]: BFV relinearisation keyswitch, N=2^14, 8 primes, base-4 digits (D = 241 digit polynomials).
+        # One GPU: tfb_keyswitch.  N GPUs (N | 8): ONE ciphertext batch key-switched by all ranks together with the RNS
+        # primes sharded over the ranks (tfb_keyswitch_shard) and the result rows assembled by one NCCL all-gather -- the
+        # path's only data-path collective (toyfhe.jl_b200/sharding.py).
+        if world in (1, 2, 4, 8):
+            from toyfhe_b200 import sharding as S
+            w4 = 2
+            D4 = T.ndigits(qs, w4)
+            lo4, hi4 = S.shard_range(L_Q, rank, world)
+            shard = T.Context(N_RING, qs[lo4:hi4], psis[lo4:hi4], device=local) if world > 1 else cq
+            krows = shard.sample_uniform(99, 1, (D4, 2))                 # this rank's rows of a (synthetic) evaluation key, NTT domain
+            c4 = {}
+            for B4 in (1, 8):
+                ct4 = cq.sample_uniform(7, 100 + B4, (B4, 3))           # the same ciphertexts on every rank (same seed and stream id)
+                if world > 1:
+                    run4 = lambda: S.keyswitch_residue_sharded(lambda a, b: cq.keyswitch_shard(shard, a, krows, ct4, w4), L_Q)
+                else:
+                    run4 = lambda: cq.keyswitch(krows, ct4, w4)
+                for _ in range(3):
+                    run4()
+                barrier()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                for _ in range(10):
+                    r4 = run4()
+                k1.record()
+                barrier()
+                tk = torch.tensor([k0.elapsed_time(k1) / 10], dtype=torch.float64, device=f"cuda:{local}")
+                if world > 1:
+                    dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+                ms4 = float(tk.item())
+                c4[f"batch{B4}"] = {"ms_per_call": ms4, "keyswitches_per_s": B4 / (ms4 * 1e-3)}
+            # (bit-exactness of the sharded path against the whole-ring call: tests/test_gpu_multi.py, tests/test_sharding_gloo.py)
+            configs["c4_keyswitch_base4"] = {
+                "workload": f"BFV relinearisation keyswitch, N=2^14, L=8x60-bit, relin_window=2 (D={D4} digit polynomials of 8 prime rows), "
+                            + ("residues sharded over the ranks: tfb_keyswitch_shard + one NCCL all-gather of the result rows per call"
+                               if world > 1 else "one GPU: tfb_keyswitch"),
+                "sharding": "residue-parallel (strong scaling of ONE ciphertext batch)" if world > 1 else "none",
+                "data_path_collective": "all_gather_into_tensor of [B][2][L/N][N] u64 per call" if world > 1 else None, **c4}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

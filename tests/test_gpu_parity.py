@@ -665,3 +665,26 @@ def test_base_conversion_specialisations_agree(generic, q8, psi8):
         assert np.array_equal(H(cq.bfv_mul(cb, 65537, cq.to_device(c1), cq.to_device(c2))), CO.bfv_mul(oq, ob, 65537, c1, c2))
     finally:
         T.force_generic(False)
+
+
+def test_one_context_from_two_streams_and_two_devices_guard():
+    """the scratch of a context is ordered across streams by the library (include/toyfhe_b200.h "Threading"): composite
+    operations issued alternately on two streams, without any synchronisation in between, give the single-stream results;
+    and every call leaves the caller's current device as it found it"""
+    import torch
+    N = 4096
+    qs, psis, ctx, orc = _ring(N, [60, 60, 40])
+    rng = np.random.default_rng(11)
+    a, b = _rand(rng, N, qs, (6, 2)), _rand(rng, N, qs, (6, 2))
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    want = orc.ct_tensor(a, b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(6):                                   # ct_tensor stages its transforms in the context's scratch
+        st = s1 if i % 2 == 0 else s2
+        outs.append(ctx.ct_tensor(da[i:i + 1], db[i:i + 1], stream=st))
+    torch.cuda.synchronize()
+    for i in range(6):
+        assert np.array_equal(H(outs[i]), want[i:i + 1]), i
+    assert torch.cuda.current_device() == ctx.device
