@@ -688,3 +688,30 @@ def test_one_context_from_two_streams_and_two_devices_guard():
     for i in range(6):
         assert np.array_equal(H(outs[i]), want[i:i + 1]), i
     assert torch.cuda.current_device() == ctx.device
+
+
+@pytest.mark.parametrize("logN,logqs,B,comps", [(12, [60, 40, 40, 60], 5, 2), (13, [60, 40, 40, 40, 40, 40, 60], 40, 2), (14, [60, 60, 40, 60], 20, 3),
+                                                (13, [40, 40, 60], 3, 3)])
+def test_crt_digits_formed_inside_the_transform(logN, logqs, B, comps):
+    """CRT keyswitch (relin_window = 0, special prime) at N = 2^12 .. 2^14: the digit polynomials are formed while the forward
+    transform loads its rows (60-bit residues re-embedded under 40-bit primes take the Barrett branch) -- same result as
+    the separate digit kernel + transform (force_generic), which test_keyswitch_* and tests/test_reference_transcriptions.py
+    pin to the oracle and to the Julia transcription"""
+    N = 1 << logN
+    key_qs, key_psis = T.prime_chain(N, logqs)
+    qs, psis = key_qs[:-1], key_psis[:-1]
+    ctx, ext = T.Context(N, qs, psis), T.Context(N, key_qs, key_psis)
+    rng = np.random.default_rng(logN + B)
+    key = ext.ntt_fwd(ext.to_device(_rand(rng, N, key_qs, (len(key_qs), 2))))
+    ct = _rand(rng, N, qs, (B, comps))
+    ct[0, -1, :, 0] = [q // 2 for q in qs]
+    ct[0, -1, :, 1] = [q // 2 + 1 for q in qs]
+    ct[0, -1, :, 2] = [q - 1 for q in qs]
+    d = ctx.to_device(ct)
+    fused = H(ctx.keyswitch(key, d, 0, ext=ext))
+    T.force_generic(1)
+    try:
+        plain = H(ctx.keyswitch(key, d, 0, ext=ext))
+    finally:
+        T.force_generic(0)
+    assert np.array_equal(fused, plain)

@@ -716,6 +716,9 @@ static int ks_digits_dual(tfb_ctx* c, tfb_ctx* r, uint32_t w, const u64* cend, u
     if (w == 0) {   // CRT digits of 2^15-position rows: extraction fused with the first global level of the transform
         rc = launch_ks_crt_ntt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
         if (rc != -1) return rc;
+        // N = 2^12 .. 2^14: digits formed in the transform's load phase (no digit rows written and re-read)
+        rc = g_force_generic ? -1 : launch_ntt_crt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+        if (rc != -1) return rc;
     }
     bool small = w > 0 && w < 62;
     for (u32 i = 0; small && i < r->L; i++) small = (1ull << w) <= r->q[i];

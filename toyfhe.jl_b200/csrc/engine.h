@@ -124,6 +124,8 @@ int ntt4_setup_device();
 int launch_ntt_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaStream_t st);
 int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t st);
 int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStream_t st);   // src: v3k::NttSrc
+int launch_ntt_s_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);
+int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);   // ntt_kernels3.cu
 // forward transform of `polys` polynomials of c->L rows each: rows [0, lq) of polynomial p from base0 (p < polys0) or base1,
 // rows [lq, c->L) from ext [polys][c->L - lq][N]; out contiguous.  -1: kernel family not applicable.
 int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0, u32 lq, const u64* ext, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu

@@ -137,6 +137,42 @@ TFB_HD void pass1(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3& rp
 #pragma unroll
     for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
 }
+// pass 1 on a CRT keyswitch digit (rlwe_she.jl:326-329): the row in shared memory holds residues modulo q_k of the
+// ciphertext's last component; the digit polynomial under this row's target prime is the CENTRED residue
+// (signedmod.jl:12-19: c > q_k / 2 ? c - q_k : c) re-embedded modulo the target prime -- formed here, in registers, while
+// the row is loaded, so the digit rows are never written to and re-read from HBM.  `br_hi` = floor(2^128 / p) high word of
+// the target prime (one-word Barrett, needed only when q_k / 2 >= p: uniform per row).
+template <int R>
+TFB_HD void pass1_crt(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3& rp, const u32 t, const u64 qk, const u64 br_hi) {
+    const u64 hq = qk >> 1, p = rp.q;
+    if (hq < p) {
+        // |centred residue| <= q_k / 2 < p: the embedding is c itself or c - q_k + p (never zero, always below p)
+        const u64 d = p - qk;                          // modulo 2^64
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            const u64 c = smem[slot<R>(a, t)];
+            x[a] = c > hq ? c + d : c;
+        }
+    } else {
+        // a wide residue under a narrower prime (the 60-bit prime's digit under the 40-bit primes of a CKKS chain)
+#pragma unroll 4
+        for (int a = 0; a < 32; a++) {
+            const u64 c = smem[slot<R>(a, t)];
+            const bool neg = c > hq;
+            const u64 v = neg ? qk - c : c;
+            u64 r = v - mulhi64(v, br_hi) * p;          // [0, 3p)
+            r = csub(r, 2 * p);
+            r = csub(r, p);
+            x[a] = (neg && r) ? p - r : r;
+        }
+    }
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = 1u << (s - 1);
+    levels3<5, 0x08>(x, tw, tb, rp);
+#pragma unroll
+    for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
+}
 // pass 2 (levels 6..10): thread (a2 = t >> R, c2 = t mod RS) holds b = 0..31; bound 10 -> (reduce) 6 -> 10 -> 14 -> (reduce) 6 -> 10
 template <int R>
 TFB_HD void pass2(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3& rp, const u32 t, const u32 s0, const u32 blk) {

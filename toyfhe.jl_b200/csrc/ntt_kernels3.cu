@@ -319,3 +319,12 @@ int launch_ntt_fwd_cross(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, 
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
+
+// CRT keyswitch digits formed inside the forward transform's load phase (N = 2^12 .. 2^14; ntt_core3.cuh pass1_crt).
+// -1: not applicable (the caller extracts the digit rows and transforms them).
+int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    if (!r->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || g_ntt_version != 3 || r->logN < 12 || r->logN > 14 || c->N != r->N) return -1;
+    if (k0 + dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
+    if (r->logN == 14) return v3k::launch_crt<4>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+    return launch_ntt_s_crt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+}

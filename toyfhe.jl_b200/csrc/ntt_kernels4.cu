@@ -30,3 +30,9 @@ int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStr
     if (c->logN == 13) return v3k::launch_s<3>(c, nullptr, out, rows, false, st, 1, s);
     return -1;
 }
+
+int launch_ntt_s_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    if (r->logN == 12) return v3k::launch_crt<2>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+    if (r->logN == 13) return v3k::launch_crt<3>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
+    return -1;
+}

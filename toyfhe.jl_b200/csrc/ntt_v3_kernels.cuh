@@ -97,11 +97,25 @@ __device__ __forceinline__ const u64* src_row(const u64* in, const NttSrc& src, 
     return src.ext + ((u64)p * (src.lj - src.lq) + (i - src.lq)) * Geo::N;
 }
 
-template <int R, bool S0ZERO>
+// CRT keyswitch digits formed inside the transform (CRT = true, s0 = 0): unit = (b * dn + kk) * L + j is digit k0 + kk of
+// ciphertext b under target prime j; its source row is residue row k0 + kk of that ciphertext's last component.
+struct CrtDig {
+    const u64* cend;
+    u64 ct_stride;
+    const PrimeParams* ppq;   // primes of the ciphertext ring (source)
+    u32 k0, dn;
+};
+template <int R>
+__device__ __forceinline__ const u64* crt_row(const CrtDig& cd, const u32 unit, const u32 L) {
+    const u32 d = unit / L;                        // (b, kk)
+    return cd.cend + (u64)(d / cd.dn) * cd.ct_stride + (u64)(cd.k0 + d % cd.dn) * NttGeo<R>::N;
+}
+
+template <int R, bool S0ZERO, bool CRT = false>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
                  const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits, const u32 in_div,
-                 const NttSrc src) {
+                 const NttSrc src, const CrtDig cd = CrtDig()) {
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ __align__(8) u64 bar;
@@ -115,11 +129,13 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
+    __shared__ u64 crt_q[CRT ? TFB_MAX_L : 1];   // source primes of the digits (CRT): read from shared memory, not through a dependent global load per row
+    if (CRT && t < cd.dn) crt_q[t] = cd.ppq[cd.k0 + t].pc.q;
     build_redtab(redtab, pp, L, t, Geo::T);
     __syncthreads();
     // in_div > 1 (s0 = 0 only): input row = unit / in_div -- one small-integer polynomial (a keyswitch digit) is
     // transformed under in_div consecutive primes without being replicated in memory first
-    if (t < 32 && unit < nunits) tma_load_row_skewed<R>(smem, src_row<R>(in, src, unit, in_div, s0, nrow), &bar, t);
+    if (t < 32 && unit < nunits) tma_load_row_skewed<R>(smem, CRT ? crt_row<R>(cd, unit, L) : src_row<R>(in, src, unit, in_div, s0, nrow), &bar, t);
     u32 parity = 0;
     u64 x[32];
     for (; unit < nunits; unit += gridDim.x) {
@@ -134,14 +150,15 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         {
             const u32 nxt = unit + gridDim.x;
             if (t < 32 && nxt < nunits) {
-                const u64* p = src_row<R>(in, src, nxt, in_div, s0, nrow);
+                const u64* p = CRT ? crt_row<R>(cd, nxt, L) : src_row<R>(in, src, nxt, in_div, s0, nrow);
                 l2_prefetch(p + t * Geo::T, Geo::T * 8);
                 if (t == 0) next_src = p;       // read back after pass 3's loads (three barriers later)
             }
         }
         mbar_wait(&bar, parity);
         parity ^= 1;
-        v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
+        if (CRT) v3::pass1_crt<R>(x, smem, tw, rp, t, crt_q[(unit / L) % cd.dn], pp[prime].pc.br_hi);
+        else v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
         __syncthreads();
         v3::pass2<R>(x, smem, tw, rp, t, s0, blk);
         __syncthreads();
@@ -294,6 +311,7 @@ template <int R>
 int setup_s() {
     const int smem = (int)v3::Lay<R>::ROW_BYTES;
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv_s_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return TFB_OK;
 }
@@ -312,6 +330,23 @@ int launch_s(tfb_ctx* c, const u64* in, u64* out, u64 rows, bool inverse, cudaSt
         NttSrc none = {};
         ntt_fwd_s_kernel<R, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(in, out, c->d_fwd, c->d_pp, c->L, 0, (u32)rows, in_div, src ? *src : none);
     }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// CRT keyswitch digits k0 .. k0+dn-1 of `cend` ([batch] ciphertexts, ct_stride words apart, residues modulo the primes of
+// `c`) in the NTT domain of ring r: dig [batch][dn][r->L][N], rows of exactly N = 2^(10+R) positions
+template <int R>
+int launch_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    typedef NttGeo<R> Geo;
+    const u64 rows = batch * dn * r->L;
+    if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+    const u64 slots = (u64)(r->num_sms > 0 ? r->num_sms : 148) * (512 / Geo::T);
+    const unsigned grid = (unsigned)(rows < slots ? rows : slots);
+    CrtDig cd;
+    cd.cend = cend; cd.ct_stride = ct_stride; cd.ppq = c->d_pp; cd.k0 = k0; cd.dn = dn;
+    ProfScope ps(PC_NTT_FWD, st);
+    ntt_fwd_s_kernel<R, true, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(nullptr, dig, r->d_fwd, r->d_pp, r->L, 0, (u32)rows, 1, NttSrc(), cd);
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }
