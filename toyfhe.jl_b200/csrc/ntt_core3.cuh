@@ -292,16 +292,22 @@ TFB_HD void pass1_store(const u64* x, u64* smem, const u32 t) {
 }
 
 // ------------------------------------------------------------------ inverse (pow2_cyc_rings.jl:308-318)
-// GS butterfly  X' = X + Y, Y' = (X - Y) w.  Products come back in [0,4q) (shoup_lazy4), so every level after the
-// first brings the sum back with the same table: k is estimated from the high words only (it can be one short of
-// floor((X+Y)/2^b), which leaves X' in (0,3q) instead of (0,2q)), and the constant is added inside the 3-input
-// sum.  Inputs of a reducing level are < 4q, of the first level canonical; X - Y + 4q < 8q.
+// GS butterfly  X' = X + Y, Y' = (X - Y) w.  Products come back in [0,3q) (shoup_lazy4) and sums double, so a value
+// has to be brought back before it passes 16q ~ 2^64.  Bounds in units of q:
+//   plain level (RED = false): inputs < 4:  X' = X + Y < 2 max(in),  D = X - Y + 4q < 8,    Y' < 3
+//   reducing level (RED = true): inputs < 6: D = X - Y + 8q < 14, and X' = X + Y + tab8[k] with k = floor estimate of
+//     (X + Y) / 2^b from the high words only (it can be one short, which leaves X' in (0,3q) instead of (0,2q)); the
+//     constant is added inside the 3-input sum.
+// From canonical input the schedule plain, plain, reduce, plain, reduce, ... keeps every value below 6q; round 1 reduced
+// at EVERY level after the first (one table lookup, one shift, two adds per butterfly on 12 of 13 ladder levels -- now
+// on 6 of 13), see the per-pass masks below.
 template <bool RED>
 TFB_HD void gs_bfly3(u64& X, u64& Y, const tw_t w, const Red3& rp) {
     const u64 x = X, y = Y;
-    const u64 d = x - y + rp.q4;
+    const u64 off = RED ? 2 * rp.q4 : rp.q4;
+    const u64 d = x - y + off;
 #ifndef __CUDA_ARCH__
-    if (y >= rp.q4 || (((u128)x + rp.q4) >> 64) != 0 || (((u128)x + y) >> 64) != 0) g_emu_overflow3++;
+    if (y >= off || (((u128)x + off) >> 64) != 0 || (((u128)x + y) >> 64) != 0) g_emu_overflow3++;
 #endif
     if (RED) {
         const u32 k = ((u32)(x >> 32) + (u32)(y >> 32)) >> rp.shb;
@@ -314,11 +320,14 @@ TFB_HD void gs_bfly3(u64& X, u64& Y, const tw_t w, const Red3& rp) {
 #endif
     } else {
         X = x + y;
+#ifndef __CUDA_ARCH__
+        if (X >= 6 * rp.q) g_emu_overflow3++;     // a plain level's output must be admissible for a reducing level
+#endif
     }
     Y = shoup_lazy4(d, w.w, w.wp, rp.q, rp.ne, rp.shb);
 }
-// levels LV..FIRST of the inverse ladder; the level executed first reduces iff RED_TOP, all later ones always
-template <int LV, int FIRST, bool RED_TOP>
+// levels LV..FIRST of the inverse ladder; the e-th level executed (e = 0 for level LV) reduces iff bit e of REDMASK is set
+template <int LV, int FIRST, u32 REDMASK>
 TFB_HD void gs_levels3(u64* x, const tw_t* __restrict__ tw, const u32* tb, const Red3& rp, const u32 js = 1) {
 #pragma unroll
     for (int u = LV; u >= FIRST; u--) {
@@ -328,12 +337,18 @@ TFB_HD void gs_levels3(u64* x, const tw_t* __restrict__ tw, const u32* tb, const
             const tw_t w = tw[tb[u - 1] + j * js];
 #pragma unroll
             for (int k = 0; k < half; k++) {
-                if (u == LV && !RED_TOP) gs_bfly3<false>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
-                else gs_bfly3<true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+                if ((REDMASK >> (LV - u)) & 1) gs_bfly3<true>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
+                else gs_bfly3<false>(x[j * 2 * half + k], x[j * 2 * half + k + half], w, rp);
             }
         }
     }
 }
+// Reduction schedules (bit e = the e-th level executed in the pass).  Pass 3 starts from canonical input: plain, plain,
+// reduce, plain (bounds 1 -> 3 -> 6 -> 3 -> 6; fewer levels for smaller rows).  Pass 2 takes anything below 6q: reduce,
+// plain, reduce, plain, reduce (-> 3).  Pass 1 takes values below 3q: plain, reduce, plain, reduce (-> 3), so the final
+// level's X - Y + 4q is valid; the five sub-block levels of longer rows: plain, reduce, plain, reduce, plain (-> 6 < 16q
+// for the canonicalising table).
+constexpr u32 INV_P3MASK = 0x4, INV_P2MASK = 0x15, INV_P1MASK = 0xA, INV_P1ALLMASK = 0xA;
 // pass 3 (levels 10+R..11): natural-order canonical input from the flat copy in shared memory
 template <int R>
 TFB_HD void inv_pass3_load(u64* x, const u64* smem, const u32 t) {
@@ -355,7 +370,7 @@ TFB_HD void inv_pass3_compute_store(u64* x, u64* smem, const tw_t* __restrict__ 
         u32 tb[R];
 #pragma unroll
         for (int u = 1; u <= R; u++) tb[u - 1] = pass3_base<R>(blk, (u32)g, u, t);
-        gs_levels3<R, 1, false>(x + g * Geo::RS, itwc, tb, rp, Geo::T);
+        gs_levels3<R, 1, INV_P3MASK>(x + g * Geo::RS, itwc, tb, rp, Geo::T);
 #ifdef __CUDA_ARCH__
 #pragma unroll
         for (int c = 0; c < (int)Geo::RS; c += 2)
@@ -376,7 +391,7 @@ TFB_HD void inv_pass2(u64* x, u64* smem, const tw_t* __restrict__ itw, const Red
     u32 tb[5];
 #pragma unroll
     for (int u = 1; u <= 5; u++) tb[u - 1] = (1u << (s0 + 4 + u)) + (blk << (4 + u)) + (a2 << (u - 1));
-    gs_levels3<5, 1, true>(x, itw, tb, rp);
+    gs_levels3<5, 1, INV_P2MASK>(x, itw, tb, rp);
 #pragma unroll
     for (int b = 0; b < 32; b++) base[b * Geo::RS] = x[b];
 }
@@ -393,7 +408,7 @@ TFB_HD void inv_pass1_compute_store(u64* x, u64* __restrict__ orow, const tw_t* 
     u32 tb[5];
 #pragma unroll
     for (int s = 1; s <= 5; s++) tb[s - 1] = 1u << (s - 1);
-    gs_levels3<5, 2, true>(x, itw, tb, rp);
+    gs_levels3<5, 2, INV_P1MASK>(x, itw, tb, rp);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const u64 U = x[k], V = x[k + 16];
@@ -411,6 +426,6 @@ TFB_HD void inv_pass1_levels_all(u64* x, const tw_t* __restrict__ itw, const Red
     u32 tb[5];
 #pragma unroll
     for (int s = 1; s <= 5; s++) tb[s - 1] = (1u << (s0 + s - 1)) + (blk << (s - 1));
-    gs_levels3<5, 1, true>(x, itw, tb, rp);
+    gs_levels3<5, 1, INV_P1ALLMASK>(x, itw, tb, rp);
 }
 }  // namespace v3
