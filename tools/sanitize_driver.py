@@ -51,3 +51,36 @@ u = cq.sample_uniform(1, 2, (2,))
 g = cq.sample_gaussian(3.2, 1, 3, (2,))
 torch.cuda.synchronize()
 print("keyswitch / keyswitch_shard / rescale / encode / decode / samplers ran", flush=True)
+# ---- round-2 kernels: gathered forward transform (ct_tensor, BFV joint basis with compact expansions), last global level on
+# load (N = 2^15 out of place), CRT digits formed inside the transform, broadcast plaintext multiply / add
+N = 4096
+allq, allpsi = T.prime_chain(N, [60] * 10)
+cq, cb = T.Context(N, allq[:3], allpsi[:3]), T.Context(N, allq[3:], allpsi[3:])
+oq, ob = CO.Rns(N, allq[:3], allpsi[:3]), CO.Rns(N, allq[3:], allpsi[3:])
+c1, c2 = rnd(rng, allq[:3], (5, 2), N), rnd(rng, allq[:3], (5, 2), N)
+assert np.array_equal(H(cq.ct_tensor(cq.to_device(c1), cq.to_device(c2))), oq.ct_tensor(c1, c2))
+assert np.array_equal(H(cq.bfv_mul(cb, 65537, cq.to_device(c1), cq.to_device(c2))), CO.bfv_mul(oq, ob, 65537, c1, c2))
+print("gathered forward transforms ok", flush=True)
+N = 1 << 15
+qs, psis = T.prime_chain(N, [40, 60])
+ctx, orc = T.Context(N, qs, psis), CO.Rns(N, qs, psis)
+a = rnd(rng, qs, (40,), N)
+f = ctx.ntt_fwd(ctx.to_device(a))
+assert np.array_equal(H(f[:2]), orc.nntt(a[:2])) and np.array_equal(H(ctx.ntt_inv(f)), a)
+print("2^15 forward with the last global level on load ok", flush=True)
+N = 1 << 13
+kq, kp = T.prime_chain(N, [60, 40, 40, 60])
+ctx, ext = T.Context(N, kq[:-1], kp[:-1]), T.Context(N, kq, kp)
+key = ext.ntt_fwd(ext.to_device(rnd(rng, kq, (4, 2), N)))
+ct = ctx.to_device(rnd(rng, kq[:-1], (30, 2), N))
+fused = ctx.keyswitch(key, ct, 0, ext=ext)
+T.force_generic(1)
+plain = ctx.keyswitch(key, ct, 0, ext=ext)
+T.force_generic(0)
+assert torch.equal(fused, plain)
+p = ctx.to_device(rnd(rng, kq[:-1], (), N))
+acc = ctx.mul_plain(ct, p)
+ctx.mul_plain(ct, p, out=acc, accumulate=True)
+ctx.add_plain_first(acc, p)
+torch.cuda.synchronize()
+print("CRT digits inside the transform / mul_plain / add_plain ok", flush=True)
