@@ -283,6 +283,33 @@ def run_ours(args):
     ntt_polys = 2 * B
     ntt_bytes = ntt_polys * L_Q * N_RING * 8 * 2
 
+    def rate(fn, reps):
+        for _ in range(3):
+            fn()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            fn()
+        a1.record(stream)
+        barrier()
+        tms = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item())
+
+    # inverse NTT at the same shape, and both directions at N = 2^15 on the CKKS chain of BASELINE configs[2]
+    # (60 + 9 x 40 + special 60 bits: 11 primes, 96 polynomials = 264 MiB per direction, out of place)
+    inv_ms = rate(lambda: cq.ntt_inv(ntt_in, out=ntt_out, stream=stream), KN)
+    q15, p15 = T.prime_chain(2 ** 15, [60] + [40] * 9 + [60])
+    c15 = T.Context(2 ** 15, q15, p15, device=local)
+    x15 = c15.sample_uniform(5, 1, (96,))
+    y15 = torch.empty_like(x15)
+    f15_ms = rate(lambda: c15.ntt_fwd(x15, out=y15, stream=stream), KN)
+    i15_ms = rate(lambda: c15.ntt_inv(x15, out=y15, stream=stream), KN)
+    bytes15 = 96 * len(q15) * (2 ** 15) * 8 * 2
+    del x15, y15
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     Be = B   # the same batch as the device-resident step
     p1 = torch.from_numpy(rand_ct(rng, qs, (Be, 2)).view(np.int64)).pin_memory()
@@ -412,6 +439,10 @@ def run_ours(args):
                     "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg[dom] // max(1, kernels[dom]["launches"] // K),
                     "peak_source": peak_src, "share_of_step": kernels[dom]["share"],
+                    # the bound that actually binds: 30.9 FMA-heavy pipe cycles per warp-butterfly in the SASS of this kernel
+                    # (IMAD.WIDE/IMAD.HI 4, IMAD 2), 896 warp-butterflies per SM sub-partition per 2^14 row, 148 SMs at 1.965 GHz
+                    "pipe_ceiling_gbs": round(262144 * 148 / (896 * 30.9 / 1.965e9) / 1e9, 1),
+                    "frac_of_pipe_ceiling": round(a / (262144 * 148 / (896 * 30.9 / 1.965e9) / 1e9), 4),
                     "note": "integer work on 61-bit residues: the FMA-heavy (IMAD) pipe is 66% busy in the transforms and 87% in the "
                             "base conversions at these rates and bounds them before HBM does (DESIGN.md section 5, "
                             "profiles/r02_ncu_bfv_step.txt, profiles/r02_ntt_ablation.txt)"}
@@ -442,6 +473,12 @@ def run_ours(args):
                     "prime_rows_per_s": world * ntt_polys * L_Q / (ntt_ms * 1e-3), "ms_per_step": ntt_ms,
                     "achieved_gbs": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "frac_of_peak": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / peak,
                     "algorithmic_bytes_per_launch": ntt_bytes},
+        "ntt_inv": {"value": world * ntt_polys / (inv_ms * 1e-3), "unit": "RNS-NTT/s (N=2^14, L=8)", "ms_per_step": inv_ms,
+                    "achieved_gbs": ntt_bytes / (inv_ms * 1e-3) / 1e9, "frac_of_peak": ntt_bytes / (inv_ms * 1e-3) / 1e9 / peak},
+        "ntt_2p15": {"shape": "N=2^15, 11 primes (60 + 9x40 + 60 bits), 96 polynomials, out of place",
+                     "fwd_gbs": bytes15 / (f15_ms * 1e-3) / 1e9, "inv_gbs": bytes15 / (i15_ms * 1e-3) / 1e9,
+                     "fwd_frac_of_peak": bytes15 / (f15_ms * 1e-3) / 1e9 / peak, "inv_frac_of_peak": bytes15 / (i15_ms * 1e-3) / 1e9 / peak,
+                     "note": "per rank; forward applies the row's last global level while loading (one HBM pass less)"},
         "cpu_baseline": cpu,
         "configs": configs,
     }
