@@ -123,6 +123,12 @@ int tfb_scalar_mul(tfb_ctx* ctx, const uint64_t* a, const uint64_t* s_residues, 
  * multiply (ckksencoding.jl:106-111) over every ciphertext of a batch, and with accumulate != 0 the `result += ...` of
  * the diagonal-method matmuls (test/ckks_matmul.jl:34-42, examples/encrypted_mnist/infer.jl:142-151). */
 int tfb_mul_plain(tfb_ctx* ctx, const uint64_t* a, const uint64_t* plain, uint64_t* out, uint64_t polys, int accumulate, void* stream);
+/* linear combinations with scalar weights: out[c] = sum_{j<J} weights[c][j] * in[j] for c < C (C <= 4, J <= 63), where in[j] is
+ * the [polys][L][N] buffer in + j*in_stride_words, weights is a DEVICE array [C][J][L] of residues (weight mod q_i) and out is
+ * [C][polys][L][N].  Replaces the sums of `c * b::AbstractFloat` (ckksencoding.jl:100-103) that make up a convolution over
+ * ciphertexts (examples/encrypted_mnist/infer.jl:117-121): every input is read once for all C outputs. */
+int tfb_lincomb(tfb_ctx* ctx, const uint64_t* in, uint64_t in_stride_words, uint32_t J, const uint64_t* weights, uint32_t C, uint64_t* out,
+                uint64_t polys, void* stream);
 /* plaintext add broadcast over a batch: out[p] = a[p] + plain for p < polys, where polynomial p starts stride_words words
  * after polynomial p-1 (>= L*N, even) and plain is one [L][N] element.  `c .+ b` of ckksencoding.jl:113-125 adds the encoded
  * plaintext to the FIRST component of every ciphertext of a batch: a = out = component 0 of ciphertext 0, stride = comps*L*N. */

@@ -28,6 +28,26 @@ def test_mul_plain_broadcast_and_accumulate():
     assert np.array_equal(ctx.to_host(d), want)
 
 
+def test_lincomb_matches_scalar_mul_and_add():
+    N = 256
+    qs, psis = T.prime_chain(N, [60, 60, 40])
+    ctx = T.Context(N, qs, psis)
+    rng = np.random.default_rng(9)
+    J, Cn = 7, 3
+    stacked = np.stack([np.stack([rng.integers(0, q, size=(2, 2, N), dtype=np.uint64) for q in qs], axis=-2) for _ in range(J)])   # [J][2][2][L][N]
+    wint = rng.integers(-2 ** 45, 2 ** 45, size=(Cn, J))
+    w = np.array([[[int(v) % q for q in qs] for v in row] for row in wint], dtype=np.uint64)
+    got = ctx.to_host(ctx.lincomb(ctx.to_device(stacked), ctx.to_device(w)))
+    want = np.zeros((Cn,) + stacked.shape[1:], dtype=object)
+    for c in range(Cn):
+        for j in range(J):
+            for i, q in enumerate(qs):
+                want[c, :, :, i, :] = (want[c, :, :, i, :] + stacked[j, :, :, i, :].astype(object) * int(w[c, j, i])) % q
+    assert np.array_equal(got, want.astype(np.uint64))
+    with pytest.raises(T.EngineError):
+        ctx.lincomb(ctx.to_device(np.zeros((64, 1, 1, 3, N), dtype=np.uint64)), ctx.to_device(np.zeros((1, 64, 3), dtype=np.uint64)))
+
+
 def test_add_plain_first_component():
     N = 128
     qs, psis = T.prime_chain(N, [60, 40])

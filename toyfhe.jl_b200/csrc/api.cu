@@ -443,6 +443,16 @@ int tfb_add_plain(tfb_ctx* c, const uint64_t* a, const uint64_t* plain, uint64_t
     return launch_add_plain(c, a, plain, out, polys, stride_words, (cudaStream_t)stream);
 }
 
+int tfb_lincomb(tfb_ctx* c, const uint64_t* in, uint64_t in_stride_words, uint32_t J, const uint64_t* weights, uint32_t C, uint64_t* out,
+                uint64_t polys, void* stream) {
+    CHECK_CTX(c);
+    if (!polys) return TFB_OK;
+    CHECK_PTR(in); CHECK_PTR(weights); CHECK_PTR(out);
+    if (J < 1 || J > 63 || C < 1 || C > 4) { tfb_set_error("lincomb: need 1 <= J <= 63 terms and 1 <= C <= 4 outputs"); return TFB_EINVAL; }
+    if (in_stride_words < polys * c->L * c->N) { tfb_set_error("lincomb: input stride shorter than one input"); return TFB_EINVAL; }
+    return launch_lincomb(c, in, in_stride_words, J, weights, C, out, polys, (cudaStream_t)stream);
+}
+
 int tfb_ring_mul(tfb_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t rows, void* stream) {
     CHECK_CTX(c); CHECK_ROWS(c, rows);
     ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);

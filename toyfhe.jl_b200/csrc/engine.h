@@ -82,6 +82,7 @@ void tfb_count_launch(int n = 1);
 int launch_binop(tfb_ctx* c, int op, const u64* a, const u64* b, u64* out, u64 rows, cudaStream_t st);
 int launch_neg(tfb_ctx* c, const u64* a, u64* out, u64 rows, cudaStream_t st);
 int launch_add_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 polys, u64 stride_words, cudaStream_t st);
+int launch_lincomb(tfb_ctx* c, const u64* in, u64 in_stride, u32 J, const u64* w, u32 C, u64* out, u64 polys, cudaStream_t st);
 int launch_mul_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 polys, bool accumulate, cudaStream_t st);
 int launch_scalar_mul(tfb_ctx* c, const u64* a, const u64* s_host, u64* out, u64 rows, cudaStream_t st);
 int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 batch, cudaStream_t st);

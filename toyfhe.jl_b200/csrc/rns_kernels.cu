@@ -141,6 +141,31 @@ __global__ void add_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
     }
 }
 
+// Linear combinations of ciphertexts with scalar weights: out[c] = sum_j w[c][j] * in[j], c < C <= 4, j < J <= 63 -- the
+// convolution of examples/encrypted_mnist/infer.jl:117-121 (sum of C_Iij * weight over the 49 window offsets, 4 channels;
+// `c * b::AbstractFloat` of ckksencoding.jl:100-103 followed by `+`).  Every input element is read ONCE for all C outputs
+// and the J products of an output are summed as 128-bit integers (J * q^2 < 2^128) and reduced once; the per-term
+// scalar-multiply + add sequence it replaces moved 3 polynomial passes per (c, j).
+// in: J buffers `in_stride` words apart, each [polys][L][N]; w: device [C][J][L] residues; out: [C][polys][L][N].
+template <int C>
+__global__ void lincomb_kernel(const u64* __restrict__ in, const u64 in_stride, const u32 J, const u64* __restrict__ w, u64* __restrict__ out,
+                               const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total) {
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 prime = (u32)((idx >> logN) % L);
+        acc128 a[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) a[c] = {0, 0};
+        for (u32 j = 0; j < J; j++) {
+            const u64 x = in[(u64)j * in_stride + idx];
+#pragma unroll
+            for (int c = 0; c < C; c++) mac128(a[c], x, w[((u64)c * J + j) * L + prime]);
+        }
+        const PrimeConst pc = pp[prime].pc;
+#pragma unroll
+        for (int c = 0; c < C; c++) out[(u64)c * total + idx] = red128_full(a[c], pc);
+    }
+}
+
 static inline unsigned grid_for(u64 work, unsigned tb) {
     u64 nb = (work + tb - 1) / tb;
     const u64 cap = 148ull * 16;
@@ -179,6 +204,21 @@ int launch_add_plain(tfb_ctx* c, const u64* a, const u64* plain, u64* out, u64 p
     const unsigned tb = 256, nb = grid_for(total2, tb);
     ProfScope ps(PC_ELEMENTWISE, st);
     add_plain_kernel<<<nb, tb, 0, st>>>((const ulonglong2*)a, (const ulonglong2*)plain, (ulonglong2*)out, c->d_pp, c->L, c->logN, stride_words / 2, total2);
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_lincomb(tfb_ctx* c, const u64* in, u64 in_stride, u32 J, const u64* w, u32 C, u64* out, u64 polys, cudaStream_t st) {
+    if (!polys) return TFB_OK;
+    const u64 total = polys * c->L * c->N;
+    const unsigned tb = 256, nb = grid_for(total, tb);
+    ProfScope ps(PC_ELEMENTWISE, st);
+    switch (C) {
+        case 1: lincomb_kernel<1><<<nb, tb, 0, st>>>(in, in_stride, J, w, out, c->d_pp, c->L, c->logN, total); break;
+        case 2: lincomb_kernel<2><<<nb, tb, 0, st>>>(in, in_stride, J, w, out, c->d_pp, c->L, c->logN, total); break;
+        case 3: lincomb_kernel<3><<<nb, tb, 0, st>>>(in, in_stride, J, w, out, c->d_pp, c->L, c->logN, total); break;
+        default: lincomb_kernel<4><<<nb, tb, 0, st>>>(in, in_stride, J, w, out, c->d_pp, c->L, c->logN, total); break;
+    }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

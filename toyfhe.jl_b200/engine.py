@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "tfb_prime_chain", "tfb_minimal_primitive_root", "tfb_ndigits",
     "tfb_ctx_create", "tfb_ctx_destroy", "tfb_ctx_info",
     "tfb_malloc", "tfb_free", "tfb_memcpy_h2d", "tfb_memcpy_d2h", "tfb_sync",
-    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain", "tfb_add_plain",
+    "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain", "tfb_add_plain", "tfb_lincomb",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
     "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
@@ -240,6 +240,17 @@ class Context:
         out = self.empty(a.shape) if out is None else out
         _check(self._lib.tfb_mul_plain(self.h, _ptr(a), _ptr(plain), _ptr(out), C.c_uint64(self._polys(a)), C.c_int(1 if accumulate else 0),
                                        _stream_ptr(stream, self.device)))
+        return out
+
+    def lincomb(self, stacked, weights, out=None, stream=None):
+        """out[c] = sum_j weights[c][j] * stacked[j]: stacked [J][..][L][N] (one contiguous tensor), weights a device int64 tensor
+        [C][J][L] of residues; out [C][..][L][N]"""
+        J, Cn = stacked.shape[0], weights.shape[0]
+        assert stacked.is_contiguous() and weights.is_contiguous() and tuple(weights.shape) == (Cn, J, self.L)
+        polys = self._polys(stacked[0])
+        out = self.empty((Cn,) + tuple(stacked.shape[1:])) if out is None else out
+        _check(self._lib.tfb_lincomb(self.h, _ptr(stacked), C.c_uint64(stacked[0].numel()), C.c_uint32(J), _ptr(weights), C.c_uint32(Cn),
+                                     _ptr(out), C.c_uint64(polys), _stream_ptr(stream, self.device)))
         return out
 
     def add_plain_first(self, ct, plain, stream=None):

@@ -104,6 +104,7 @@ class MnistPipeline:
         self.pipe = Pipeline(self.params)
         self.model = make_model(seed, m)
         self._diags = None
+        self._conv_w = None
 
     def encrypt_inputs(self, I: np.ndarray) -> List[CtBatch]:
         """C_Iij = encrypt(kp, CKKSEncoding(vec(I_ij))) (infer.jl:112-116): 49 batches of one ciphertext"""
@@ -113,6 +114,16 @@ class MnistPipeline:
                 slots = I[i, j].T.reshape(-1)                           # slot k + n_img * l (column-major vec of [k][l])
                 c = T.encrypt(self.s, self.kp, T.CKKSEncoding(SCALE, slots.astype(np.complex128)))
                 out.append(CtBatch.from_ciphertexts(self.pipe, [c]))
+        return out
+
+    def stack_inputs(self, C: List[CtBatch], batch: int) -> List[CtBatch]:
+        """the 49 input batches replicated to `batch` pipelines as slices of ONE tensor [49][batch][2][L][N]"""
+        stack = torch.stack([c.replicate(batch).ct for c in C]).contiguous()
+        out = []
+        for i, c in enumerate(C):
+            b = CtBatch(self.pipe, c.drops, stack[i], c.scale)
+            b.stack = stack
+            out.append(b)
         return out
 
     def diagonals(self, scale1: float, scale2: float):
@@ -127,18 +138,30 @@ class MnistPipeline:
 
     def forward(self, C: List[CtBatch]) -> CtBatch:
         mdl, n_img = self.model, self.n_img
-        # convolution: 4 channels x 49 ct*scalar, + bias, rescale
+        # convolution: 4 channels x 49 ct*scalar summed (+ bias, rescale).  When the 49 input batches are slices of one
+        # stacked tensor (encrypt_inputs_stacked) all 196 products are ONE launch that reads every input once (tfb_lincomb)
         conved = []
-        for ch in range(CHANNELS):
-            acc = None
-            for i in range(KS):
-                for j in range(KS):
-                    w = float(mdl["conv_w"][i, j, ch])
-                    if acc is None:
-                        acc = C[i * KS + j].mul_scalar(w)
-                    else:
-                        C[i * KS + j].mul_scalar(w, out=acc, accumulate=True)
-            conved.append(acc.add_plain(mdl["conv_b"][ch]).rescale())
+        base = getattr(C[0], "stack", None)
+        if base is not None and all(getattr(c, "stack", None) is base for c in C):
+            lvl = C[0].lvl
+            if self._conv_w is None:
+                s_int = [[int(round(float(mdl["conv_w"][i, j, ch]) * C[0].scale)) for i in range(KS) for j in range(KS)] for ch in range(CHANNELS)]
+                self._conv_w = lvl.ctx.to_device(np.array([[[s % q for q in lvl.ring.qs] for s in row] for row in s_int], dtype=np.uint64))
+            outs = lvl.ctx.lincomb(base, self._conv_w)                                   # [4][B][2][L][N]
+            for ch in range(CHANNELS):
+                acc = CtBatch(self.pipe, C[0].drops, outs[ch], C[0].scale * C[0].scale)
+                conved.append(acc.add_plain(mdl["conv_b"][ch]).rescale())
+        else:
+            for ch in range(CHANNELS):
+                acc = None
+                for i in range(KS):
+                    for j in range(KS):
+                        w = float(mdl["conv_w"][i, j, ch])
+                        if acc is None:
+                            acc = C[i * KS + j].mul_scalar(w)
+                        else:
+                            C[i * KS + j].mul_scalar(w, out=acc, accumulate=True)
+                conved.append(acc.add_plain(mdl["conv_b"][ch]).rescale())
         sq1 = [x.square_relin(self.ek).rescale() for x in conved]
         # the matmul operands are encoded at the scales the ciphertexts have at their levels: known once these exist
         if self._diags is None:
@@ -188,7 +211,7 @@ def run(batch: int, m: int, N: int, check: bool = True, reps: int = 1, seed: int
         out.update({"max_abs_err": err, "max_abs_value": float(np.max(np.abs(want))),
                     "labels_agree": bool(np.array_equal(np.argmax(got, axis=0), np.argmax(want, axis=0)))})
     if batch > 0:
-        C = [c.replicate(batch) for c in C1]
+        C = P.stack_inputs(C1, batch)
         launches0 = T.kernel_launches()
         P.forward(C)                                                  # warm-up (allocations, operand encodes)
         torch.cuda.synchronize()
