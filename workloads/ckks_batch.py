@@ -195,18 +195,28 @@ class Graphed:
     one B200: 172 -> 595 pipelines/s; results bit-identical, tests/test_gpu_workloads.py)."""
 
     def __init__(self, fn):
-        self.fn, self.graph, self.out = fn, None, None
+        self.fn, self.graph, self.out, self.eager = fn, None, None, False
 
     def __call__(self):
+        if self.eager:
+            return self.fn()
         if self.graph is None:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 self.fn()
             side.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
-                self.out = self.fn()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.out = self.fn()
+                self.graph = g
+            except Exception as e:       # capture refused (driver / allocator state): same results from the eager path, only slower
+                import warnings
+                warnings.warn(f"CUDA graph capture failed ({e}); running the launch sequence eagerly")
+                torch.cuda.synchronize()
+                self.eager = True
+                return self.fn()
         self.graph.replay()
         return self.out
 
