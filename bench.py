@@ -369,8 +369,9 @@ def run_ours(args):
             D4 = T.ndigits(qs, w4)
             lo4, hi4 = S.shard_range(L_Q, rank, world)
             shard = T.Context(N_RING, qs[lo4:hi4], psis[lo4:hi4], device=local) if world > 1 else cq
-            krows = shard.sample_uniform(99, 1, (D4, 2))                 # this rank's rows of a (synthetic) evaluation key, NTT domain
-            c4 = {}
+            full4 = cq.sample_uniform(99, 1, (D4, 2))                    # a (synthetic) evaluation key in the NTT domain, the same on every rank
+            krows = S.key_rows_for_shard(full4, lo4, hi4) if world > 1 else full4   # the rows this rank keeps and streams
+            c4, ok4 = {}, True
             for B4 in (1, 8):
                 ct4 = cq.sample_uniform(7, 100 + B4, (B4, 3))           # the same ciphertexts on every rank (same seed and stream id)
                 if world > 1:
@@ -391,13 +392,22 @@ def run_ours(args):
                     dist.all_reduce(tk, op=dist.ReduceOp.MAX)
                 ms4 = float(tk.item())
                 c4[f"batch{B4}"] = {"ms_per_call": ms4, "keyswitches_per_s": B4 / (ms4 * 1e-3)}
+                if world > 1:   # every rank checks the gathered result bit for bit against the whole-ring call with the whole key
+                    ok4 = ok4 and bool(torch.equal(r4, cq.keyswitch(full4, ct4, w4)))
+            del full4
+            if world > 1:
+                okt = torch.tensor([1 if ok4 else 0], dtype=torch.int32, device=f"cuda:{local}")
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                ok4 = bool(int(okt.item()))
             # (bit-exactness of the sharded path against the whole-ring call: tests/test_gpu_multi.py, tests/test_sharding_gloo.py)
             configs["c4_keyswitch_base4"] = {
                 "workload": f"BFV relinearisation keyswitch, N=2^14, L=8x60-bit, relin_window=2 (D={D4} digit polynomials of 8 prime rows), "
                             + ("residues sharded over the ranks: tfb_keyswitch_shard + one NCCL all-gather of the result rows per call"
                                if world > 1 else "one GPU: tfb_keyswitch"),
                 "sharding": "residue-parallel (strong scaling of ONE ciphertext batch)" if world > 1 else "none",
-                "data_path_collective": "all_gather_into_tensor of [B][2][L/N][N] u64 per call" if world > 1 else None, **c4}
+                "data_path_collective": "all_gather_into_tensor of [B][2][L/N][N] u64 per call" if world > 1 else None,
+                "correct": ok4, "checked": "sharded result == tfb_keyswitch over the whole ring with the whole key, on every rank" if world > 1 else "single GPU: the path the tests pin to the oracle",
+                **c4}
 
     if rank != 0:
         if world > 1:
