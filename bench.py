@@ -372,9 +372,19 @@ def run_ours(args):
             full4 = cq.sample_uniform(99, 1, (D4, 2))                    # a (synthetic) evaluation key in the NTT domain, the same on every rank
             krows = S.key_rows_for_shard(full4, lo4, hi4) if world > 1 else full4   # the rows this rank keeps and streams
             c4, ok4 = {}, True
-            for B4 in (1, 8):
+            xchg, xchg_note = None, None
+            if world > 1:
+                try:    # result slots of every rank mapped into every other rank (CUDA IPC, NVLink peer memory)
+                    xchg = S.open_peer_exchange(cq, L_Q, 8)
+                except Exception as e:   # no IPC between the ranks (container policy): the NCCL all-gather path below still runs
+                    xchg_note = f"unavailable: {e}"
+            for B4, mode4 in ((1, ""), (8, ""), (1, "_push"), (8, "_push")):
+                if mode4 and xchg is None:
+                    continue
                 ct4 = cq.sample_uniform(7, 100 + B4, (B4, 3))           # the same ciphertexts on every rank (same seed and stream id)
-                if world > 1:
+                if world > 1 and mode4:   # the epilogue kernel stores this rank's rows into every rank's slot and waits on the peers' flags
+                    run4 = lambda: S.keyswitch_residue_sharded_push(cq, shard, lo4, krows, ct4, w4, xchg)
+                elif world > 1:           # shard kernels, then one NCCL all-gather of the result rows
                     run4 = lambda: S.keyswitch_residue_sharded(lambda a, b: cq.keyswitch_shard(shard, a, krows, ct4, w4), L_Q)
                 else:
                     run4 = lambda: cq.keyswitch(krows, ct4, w4)
@@ -391,10 +401,14 @@ def run_ours(args):
                 if world > 1:
                     dist.all_reduce(tk, op=dist.ReduceOp.MAX)
                 ms4 = float(tk.item())
-                c4[f"batch{B4}"] = {"ms_per_call": ms4, "keyswitches_per_s": B4 / (ms4 * 1e-3)}
+                c4[f"batch{B4}{mode4}"] = {"ms_per_call": ms4, "keyswitches_per_s": B4 / (ms4 * 1e-3)}
                 if world > 1:   # every rank checks the gathered result bit for bit against the whole-ring call with the whole key
                     ok4 = ok4 and bool(torch.equal(r4, cq.keyswitch(full4, ct4, w4)))
             del full4
+            if xchg is not None:
+                ok4 = ok4 and not xchg.timed_out()
+                dist.barrier()
+                xchg.close()
             if world > 1:
                 okt = torch.tensor([1 if ok4 else 0], dtype=torch.int32, device=f"cuda:{local}")
                 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
@@ -402,10 +416,13 @@ def run_ours(args):
             # (bit-exactness of the sharded path against the whole-ring call: tests/test_gpu_multi.py, tests/test_sharding_gloo.py)
             configs["c4_keyswitch_base4"] = {
                 "workload": f"BFV relinearisation keyswitch, N=2^14, L=8x60-bit, relin_window=2 (D={D4} digit polynomials of 8 prime rows), "
-                            + ("residues sharded over the ranks: tfb_keyswitch_shard + one NCCL all-gather of the result rows per call"
+                            + ("residues sharded over the ranks; batchB: tfb_keyswitch_shard + one NCCL all-gather of the result rows per call; "
+                               "batchB_push: tfb_keyswitch_shard_push, the epilogue kernel stores its rows into every rank's buffer over NVLink "
+                               "peer memory and waits on the peers' flags (no collective call)"
                                if world > 1 else "one GPU: tfb_keyswitch"),
                 "sharding": "residue-parallel (strong scaling of ONE ciphertext batch)" if world > 1 else "none",
                 "data_path_collective": "all_gather_into_tensor of [B][2][L/N][N] u64 per call" if world > 1 else None,
+                "peer_push": (xchg_note or "CUDA IPC-mapped result slots, fused into ks_finish_push_kernel") if world > 1 else None,
                 "correct": ok4, "checked": "sharded result == tfb_keyswitch over the whole ring with the whole key, on every rank" if world > 1 else "single GPU: the path the tests pin to the oracle",
                 **c4}
 

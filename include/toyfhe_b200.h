@@ -225,6 +225,27 @@ int tfb_keyswitch(tfb_ctx* ctx, tfb_ctx* ctx_ext, uint32_t w, const uint64_t* ke
 int tfb_keyswitch_shard(tfb_ctx* ctx, tfb_ctx* ctx_shard, uint32_t first, uint32_t w, const uint64_t* key_dual_shard, uint32_t D,
                         const uint64_t* ct, uint32_t comps, uint64_t* out_shard, uint64_t batch, void* stream);
 
+/* The same, with the exchange of the result rows fused into the last kernel (one process per GPU, NVLink peer memory
+ * instead of a collective): every rank creates an exchange (two result slots of slot_bytes >= batch*2*L*N*8 plus flag
+ * words, one cudaMalloc), the ranks swap the 64-byte IPC handles through whatever channel they have (the Python layer uses
+ * torch.distributed.all_gather_object) and attach each other's buffers.  tfb_keyswitch_shard_push then runs the sharded
+ * keyswitch and its epilogue stores this rank's rows into EVERY rank's slot, publishes a per-call epoch in the peers' flag
+ * words and waits for theirs: when the launch completes (stream order), *result -- this rank's slot of the call, valid until
+ * the call after next -- holds [batch][2][L][N], what tfb_keyswitch returns.  Every rank must make the same sequence of calls.
+ * A peer that never arrives makes the wait give up after 2 s (tfb_xchg_check reports it) instead of hanging the GPU.
+ * tfb_xchg_attach_ptr is the same-process form (threads / tests): the peer's tfb_xchg_local pointer itself.
+ * tfb_xchg_destroy: the caller first makes sure (barrier) that no peer still writes into this rank's buffer. */
+typedef struct tfb_xchg tfb_xchg;
+int tfb_xchg_create(tfb_ctx* ctx, uint32_t rank, uint32_t world, uint64_t slot_bytes, tfb_xchg** out);
+int tfb_xchg_export(tfb_xchg* x, uint8_t handle[64]);
+int tfb_xchg_attach_ipc(tfb_xchg* x, uint32_t peer, const uint8_t handle[64]);
+int tfb_xchg_attach_ptr(tfb_xchg* x, uint32_t peer, void* base);
+int tfb_xchg_local(tfb_xchg* x, void** base);
+int tfb_xchg_check(tfb_xchg* x, int* timed_out);
+int tfb_xchg_destroy(tfb_xchg* x);
+int tfb_keyswitch_shard_push(tfb_ctx* ctx, tfb_ctx* ctx_shard, uint32_t first, uint32_t w, const uint64_t* key_dual_shard, uint32_t D,
+                             const uint64_t* ct, uint32_t comps, tfb_xchg* x, uint64_t** result, uint64_t batch, void* stream);
+
 /* ---- host-buffer entry points (pinned or pageable host memory) ------------------ */
 /* Same semantics as the device versions; copies in, runs, copies out and
  * synchronises `stream` before returning. */

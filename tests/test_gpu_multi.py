@@ -96,6 +96,18 @@ def _ks_worker(rank, world, port, outdir):
         res = S.keyswitch_residue_sharded(lambda a, b: ctx.keyswitch_shard(shard, a, krows, d_ct, w), L)
         whole = ctx.keyswitch(key_dual, d_ct, w)
         assert torch.equal(res, whole)
+        # the same with the exchange fused into the epilogue kernel (peer stores over NVLink, IPC-mapped buffers): three
+        # calls in a row exercise both result slots and the epoch flags
+        x = S.open_peer_exchange(ctx, L, 2)
+        try:
+            for it in range(3):
+                ct_i = ctx.to_device(rnd((1 + it % 2, 3)))
+                got = S.keyswitch_residue_sharded_push(ctx, shard, lo, krows, ct_i, w, x)
+                assert torch.equal(got, ctx.keyswitch(key_dual, ct_i, w))
+            assert not x.timed_out()
+            dist.barrier()
+        finally:
+            x.close()
         np.save(os.path.join(outdir, f"ks{rank}.npy"), np.array([1]))
         dist.barrier()
     finally:

@@ -413,6 +413,8 @@ def test_keyswitch_digits(w):
                                              (2048, [50, 50], 1, 3), (1024, [60] * 4, 2, 3),
                                              # N = 2^12, 2^13: base-2^w digits written once and transformed under every prime
                                              (4096, [60, 60, 40], 2, 3), (4096, [50, 50], 7, 2), (8192, [60, 40, 40], 3, 3),
+                                             # N = 2^14; w = 5, 7 do not divide 64: digits that straddle two limbs of the integer
+                                             (16384, [60, 40], 5, 2), (16384, [60, 60, 60], 7, 3),
                                              # N = 2^15: CRT digits formed inside the first global level of the transform
                                              (32768, [60, 40, 40], 0, 2), (32768, [60, 40], 0, 3)])
 def test_keyswitch_plain(N, logqs, w, comps):
@@ -429,6 +431,33 @@ def test_keyswitch_plain(N, logqs, w, comps):
         c1 = ct[b, 0]
         c2 = ct[b, 1] if comps == 3 else np.zeros_like(ct[b, 0])
         w1, w2 = orc.keyswitch_accum(dg, key, c1, c2)
+        assert np.array_equal(got[b, 0], w1) and np.array_equal(got[b, 1], w2)
+
+
+@pytest.mark.parametrize("N,logqs,w,B", [(2048, [60, 60], 1, 2),      # 8 Ki coefficients: 16 digit lanes per coefficient
+                                         (4096, [60] * 4, 2, 4),      # 64 Ki: 8 lanes
+                                         (4096, [60] * 4, 2, 12),     # 192 Ki: 4 lanes
+                                         (4096, [60] * 4, 2, 24)])    # above the threshold: one thread per coefficient
+def test_keyswitch_small_batch_split_accumulate(N, logqs, w, B):
+    """One ciphertext (or a residue shard of it) has too few coefficients to fill the GPU with one thread each: the key
+    accumulation then splits the digit range over the warps of a CTA (ks_accum_split_kernel).  Same bits as the oracle and
+    as the single-thread-per-coefficient kernel."""
+    qs, psis, ctx, orc = _ring(N, logqs)
+    rng = np.random.default_rng(N + w + B)
+    D = T.ndigits(qs, w)
+    key = _rand(rng, N, qs, (D, 2))
+    ct = _rand(rng, N, qs, (B, 3))
+    key_dual = ctx.ntt_fwd(ctx.to_device(key))
+    got = H(ctx.keyswitch(key_dual, ctx.to_device(ct), w))
+    T.force_generic(1)
+    try:
+        plain = H(ctx.keyswitch(key_dual, ctx.to_device(ct), w))
+    finally:
+        T.force_generic(0)
+    assert np.array_equal(got, plain)
+    for b in range(min(B, 2)):
+        dg = orc.keyswitch_digits(ct[b, 2], w)
+        w1, w2 = orc.keyswitch_accum(dg, key, ct[b, 0], ct[b, 1])
         assert np.array_equal(got[b, 0], w1) and np.array_equal(got[b, 1], w2)
 
 

@@ -32,9 +32,15 @@ shard = T.Context(N, qs[lo:hi], psis[lo:hi], device=local)
 key_dual = ctx.ntt_fwd(ctx.to_device(rnd((D, 2))))           # every rank builds the same key, keeps only its rows
 krows = S.key_rows_for_shard(key_dual, lo, hi)
 del key_dual
-for B in (1, 8):
+xchg = S.open_peer_exchange(ctx, L, 8) if world > 1 else None        # result slots mapped into every rank (CUDA IPC over NVLink)
+for B, mode in ((1, "allgather"), (8, "allgather"), (1, "push"), (8, "push")):
+    if mode == "push" and xchg is None:
+        continue
     ct = ctx.to_device(rnd((B, 3)))
-    fn = lambda: S.keyswitch_residue_sharded(lambda a, b: ctx.keyswitch_shard(shard, a, krows, ct, w), L)
+    if mode == "allgather":   # shard kernels, then ONE NCCL all-gather of the result rows
+        fn = lambda: S.keyswitch_residue_sharded(lambda a, b: ctx.keyswitch_shard(shard, a, krows, ct, w), L)
+    else:                     # the epilogue kernel stores its rows into every rank's slot and waits for the peers' flags: no collective
+        fn = lambda: S.keyswitch_residue_sharded_push(ctx, shard, lo, krows, ct, w, xchg)
     for _ in range(3):
         out = fn()
     torch.cuda.synchronize()
@@ -51,10 +57,17 @@ for B in (1, 8):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    res[f"batch{B}"] = {"ms_per_call": round(ms, 4), "keyswitches_per_s": round(B / ms * 1e3, 1), "key_bytes_per_rank": int(krows.numel() * 8)}
+    if mode == "push":
+        same = torch.equal(out, S.keyswitch_residue_sharded(lambda a, b: ctx.keyswitch_shard(shard, a, krows, ct, w), L))
+        ok = torch.tensor([int(same and not xchg.timed_out())], device=f"cuda:{local}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        assert int(ok.item()) == 1, "push exchange result differs from the all-gather path"
+    res[f"batch{B}" + ("_push" if mode == "push" else "")] = {"ms_per_call": round(ms, 4), "keyswitches_per_s": round(B / ms * 1e3, 1), "key_bytes_per_rank": int(krows.numel() * 8)}
     if rank == 0:
-        print(f"G={world} batch {B}: {ms:.3f} ms per call = {B / ms * 1e3:.0f} keyswitches/s (key rows per rank: {krows.numel() * 8 / 2**20:.0f} MiB)", flush=True)
+        print(f"G={world} batch {B} [{mode}]: {ms:.3f} ms per call = {B / ms * 1e3:.0f} keyswitches/s (key rows per rank: {krows.numel() * 8 / 2**20:.0f} MiB)", flush=True)
 if rank == 0 and len(sys.argv) > 1:
     json.dump(res, open(sys.argv[1], "w"), indent=1)
 if world > 1:
+    dist.barrier()
+    xchg.close()
     dist.destroy_process_group()

@@ -6,11 +6,11 @@ Layout: ``csrc/`` holds the CUDA kernels and the C-ABI (include/toyfhe_b200.h);
 ``engine.py`` is the ctypes binding (the Python stand-in for the Julia ccall
 shim); ``ring.py`` / ``scheme.py`` mirror the reference's host-side interface
 (NegacyclicRing, RingElement, CipherText, keygen/encrypt/decrypt, ...)."""
-from .engine import (force_generic, ntt_version, ntt_force_harvey, ntt_max_mode, ntt_cross, ABI_SYMBOLS, LIB_PATH, Context, EngineError, kernel_launches, load_library,
+from .engine import (force_generic, ntt_version, ntt_force_harvey, ntt_max_mode, ntt_cross, ABI_SYMBOLS, LIB_PATH, Context, PeerExchange, EngineError, kernel_launches, load_library,
                      minimal_primitive_root, ndigits, prime_chain, profile_enable, profile_read)
 from ._build import build_library
 
-__all__ = ["force_generic", "ntt_version", "ntt_force_harvey", "ntt_max_mode", "ntt_cross", "ABI_SYMBOLS", "LIB_PATH", "Context", "EngineError", "kernel_launches", "load_library",
+__all__ = ["force_generic", "ntt_version", "ntt_force_harvey", "ntt_max_mode", "ntt_cross", "ABI_SYMBOLS", "LIB_PATH", "Context", "PeerExchange", "EngineError", "kernel_launches", "load_library",
            "minimal_primitive_root", "ndigits", "prime_chain", "profile_enable", "profile_read", "build_library"]
 
 from .ring import NegacyclicRing, RingElement, nntt, inntt

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 
 #include "engine.h"
 #include "ntt_core3.cuh"
@@ -732,6 +733,15 @@ static int ks_digits_dual(tfb_ctx* c, tfb_ctx* r, uint32_t w, const u64* cend, u
     }
     bool small = w > 0 && w < 62;
     for (u32 i = 0; small && i < r->L; i++) small = (1ull << w) <= r->q[i];
+    if (small && !g_force_generic && r->v3_ok && r->logN >= 12 && r->logN <= 14 && c->N == r->N) {
+        // base-2^w digits cut out of the binary limbs of the integers while the transform loads its row
+        const size_t need = (size_t)batch * c->L * c->N * sizeof(u64);
+        if ((rc = ws_reserve(r, need))) return rc;
+        u64* limbs = (u64*)r->ws;
+        if ((rc = launch_ks_limbs(c, cend, ct_stride, limbs, batch, st))) return rc;   // (once per digit chunk: chunks are 4 GiB of digit rows)
+        rc = launch_ntt_pow2(r, limbs, c->L, w, dig, k0, dn, batch, st);
+        if (rc != -1) return rc;
+    }
     if (small && r->L > 1 && r->v3_ok && r->logN >= 12 && r->logN <= 14) {
         const size_t need = (size_t)batch * dn * r->N * sizeof(u64);
         if ((rc = ws_reserve(r, need))) return rc;
@@ -785,13 +795,11 @@ int tfb_keyswitch(tfb_ctx* c, tfb_ctx* ext, uint32_t w, const uint64_t* key_dual
     return launch_ks_finish(c, ct, comps, acc, out, batch, st);
 }
 
-int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
-                        uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
-    CHECK_CTX(c); CHECK_CTX(r);
-    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
-    ScratchGuard TFB_CAT(sg_, __COUNTER__)(r, stream);
-    if (!batch) return TFB_OK;
-    CHECK_PTR(key_dual); CHECK_PTR(ct); CHECK_PTR(out);
+// everything of the sharded keyswitch up to the inverse transform: *acc_out [batch][2][Ls][N] (primal) = this rank's rows of
+// sum_k digit_k * key_k; the caller adds the ciphertext's own components (launch_ks_finish, or the peer-push epilogue)
+static int keyswitch_shard_acc(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
+                        uint32_t comps, uint64_t batch, cudaStream_t st, u64** acc_out) {
+    CHECK_PTR(key_dual); CHECK_PTR(ct);
     if (comps != 2 && comps != 3) { tfb_set_error("keyswitch: ciphertext must have 2 or 3 components"); return TFB_EINVAL; }
     if (r->N != c->N || r->L == 0 || (u64)first + r->L > c->L) { tfb_set_error("keyswitch_shard: shard primes out of range"); return TFB_EINVAL; }
     for (u32 i = 0; i < r->L; i++)
@@ -802,7 +810,6 @@ int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, cons
         if (rc) return rc;
     }
     if (D < Dneed) { tfb_set_error("keyswitch: evaluation key has too few digit components"); return TFB_EINVAL; }
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t polyr = (size_t)r->L * r->N, polyc = (size_t)c->L * c->N;
     u32 dch = (u32)((size_t)(4ull << 30) / (batch * polyr * sizeof(u64)));
     if (dch < 1) dch = 1;
@@ -818,7 +825,145 @@ int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, cons
         if ((rc = launch_ks_accum(r, k0, dn, dig, key_dual, acc, k0 ? 1 : 0, batch, st))) return rc;
     }
     if ((rc = launch_ntt(r, acc, acc, 2 * batch * r->L, true, st))) return rc;
+    *acc_out = acc;
+    return TFB_OK;
+}
+
+int tfb_keyswitch_shard(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
+                        uint32_t comps, uint64_t* out, uint64_t batch, void* stream) {
+    CHECK_CTX(c); CHECK_CTX(r);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(r, stream);
+    if (!batch) return TFB_OK;
+    CHECK_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    u64* acc;
+    int rc = keyswitch_shard_acc(c, r, first, w, key_dual, D, ct, comps, batch, st, &acc);
+    if (rc) return rc;
     return launch_ks_finish(r, ct, comps, acc, out, batch, st, c->L, first);
+}
+
+// ---------------------------------------------------------- peer exchange (sharded keyswitch, one process per GPU)
+// Local allocation: two result slots (a call writes slot epoch & 1 on every rank, so a rank that runs one call ahead never
+// overwrites rows a slower peer is still reading) + the flag words + the CTA counter and the error word.
+struct tfb_xchg {
+    tfb_ctx* ctx;
+    u32 rank, world;
+    size_t slot_words;
+    u64* local;                       // cudaMalloc: [2][slot_words] results, then TFB_MAX_PEERS flag words, then count, err
+    u64* peer[TFB_MAX_PEERS];         // the same allocation of every rank, mapped here (peer[rank] = local)
+    bool ipc[TFB_MAX_PEERS];
+    u64 epoch;
+};
+static u64* xchg_flags(const tfb_xchg* x, u32 p) { return x->peer[p] + 2 * x->slot_words; }
+
+int tfb_xchg_create(tfb_ctx* c, uint32_t rank, uint32_t world, uint64_t slot_bytes, tfb_xchg** out) {
+    CHECK_CTX(c); CHECK_PTR(out);
+    if (world < 1 || world > TFB_MAX_PEERS || rank >= world || slot_bytes == 0 || slot_bytes % 8) { tfb_set_error("xchg_create: need rank < world <= 8 and a slot size in whole words"); return TFB_EINVAL; }
+    tfb_xchg* x = new (std::nothrow) tfb_xchg();
+    if (!x) return TFB_ENOMEM;
+    x->ctx = c; x->rank = rank; x->world = world; x->slot_words = slot_bytes / 8; x->epoch = 0;
+    for (u32 p = 0; p < TFB_MAX_PEERS; p++) { x->peer[p] = nullptr; x->ipc[p] = false; }
+    const size_t bytes = 2 * slot_bytes + (TFB_MAX_PEERS + 2) * sizeof(u64);
+    cudaError_t e = cudaMalloc((void**)&x->local, bytes);
+    if (e != cudaSuccess) { delete x; return tfb_cuda_fail(e, "cudaMalloc(exchange buffer)"); }
+    e = cudaMemset(x->local, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();      // zeroed before any peer can learn the address
+    if (e != cudaSuccess) { cudaFree(x->local); delete x; return tfb_cuda_fail(e, "cudaMemset(exchange buffer)"); }
+    x->peer[rank] = x->local;
+    *out = x;
+    return TFB_OK;
+}
+int tfb_xchg_export(tfb_xchg* x, uint8_t handle[64]) {
+    if (!x) { tfb_set_error("null exchange"); return TFB_EINVAL; }
+    CHECK_CTX(x->ctx); CHECK_PTR(handle);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    TFB_CUDA(cudaIpcGetMemHandle(&h, x->local));
+    memcpy(handle, &h, 64);
+    return TFB_OK;
+}
+int tfb_xchg_attach_ipc(tfb_xchg* x, uint32_t peer, const uint8_t handle[64]) {
+    if (!x) { tfb_set_error("null exchange"); return TFB_EINVAL; }
+    CHECK_CTX(x->ctx); CHECK_PTR(handle);
+    if (peer >= x->world || peer == x->rank || x->peer[peer]) { tfb_set_error("xchg_attach: bad or repeated peer"); return TFB_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    TFB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[peer] = (u64*)p;
+    x->ipc[peer] = true;
+    return TFB_OK;
+}
+/* same process (threads, or several exchanges in one test process): the peer's local base pointer itself */
+int tfb_xchg_attach_ptr(tfb_xchg* x, uint32_t peer, void* base) {
+    if (!x) { tfb_set_error("null exchange"); return TFB_EINVAL; }
+    CHECK_CTX(x->ctx); CHECK_PTR(base);
+    if (peer >= x->world || peer == x->rank || x->peer[peer]) { tfb_set_error("xchg_attach: bad or repeated peer"); return TFB_EINVAL; }
+    cudaPointerAttributes at;
+    TFB_CUDA(cudaPointerGetAttributes(&at, base));
+    if (at.type != cudaMemoryTypeDevice) { tfb_set_error("xchg_attach: not a device pointer"); return TFB_EINVAL; }
+    if (at.device != x->ctx->device) {
+        int can = 0;
+        TFB_CUDA(cudaDeviceCanAccessPeer(&can, x->ctx->device, at.device));
+        if (!can) { tfb_set_error("xchg_attach: no peer access between the two devices"); return TFB_EUNSUPPORTED; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return tfb_cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        (void)cudaGetLastError();
+    }
+    x->peer[peer] = (u64*)base;
+    return TFB_OK;
+}
+int tfb_xchg_local(tfb_xchg* x, void** base) {
+    if (!x || !base) { tfb_set_error("null exchange"); return TFB_EINVAL; }
+    *base = x->local;
+    return TFB_OK;
+}
+/* the caller makes sure (barrier) that no peer still writes into this rank's buffer */
+int tfb_xchg_destroy(tfb_xchg* x) {
+    if (!x) return TFB_OK;
+    CHECK_CTX(x->ctx);
+    cudaDeviceSynchronize();
+    for (u32 p = 0; p < x->world; p++)
+        if (x->ipc[p]) cudaIpcCloseMemHandle(x->peer[p]);
+    cudaFree(x->local);
+    delete x;
+    return TFB_OK;
+}
+
+int tfb_keyswitch_shard_push(tfb_ctx* c, tfb_ctx* r, uint32_t first, uint32_t w, const uint64_t* key_dual, uint32_t D, const uint64_t* ct,
+                             uint32_t comps, tfb_xchg* x, uint64_t** result, uint64_t batch, void* stream) {
+    CHECK_CTX(c); CHECK_CTX(r);
+    if (!x || x->ctx->device != c->device) { tfb_set_error("keyswitch_shard_push: exchange belongs to another device"); return TFB_EINVAL; }
+    CHECK_PTR(result);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(c, stream);
+    ScratchGuard TFB_CAT(sg_, __COUNTER__)(r, stream);
+    if (!batch) { tfb_set_error("keyswitch_shard_push: empty batch (every rank must take part in the exchange)"); return TFB_EINVAL; }
+    if (batch * 2 * c->L * c->N > x->slot_words) { tfb_set_error("keyswitch_shard_push: batch larger than the exchange slot"); return TFB_EINVAL; }
+    for (u32 p = 0; p < x->world; p++)
+        if (!x->peer[p]) { tfb_set_error("keyswitch_shard_push: a peer is not attached"); return TFB_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    u64* acc;
+    int rc = keyswitch_shard_acc(c, r, first, w, key_dual, D, ct, comps, batch, st, &acc);
+    if (rc) return rc;
+    const u64 epoch = ++x->epoch;
+    u64 *outs[TFB_MAX_PEERS], *flags[TFB_MAX_PEERS];
+    for (u32 p = 0; p < x->world; p++) { outs[p] = x->peer[p] + (epoch & 1) * x->slot_words; flags[p] = xchg_flags(x, p); }
+    u32* tail = (u32*)(x->local + 2 * x->slot_words + TFB_MAX_PEERS);
+    rc = launch_ks_finish_push(r, ct, comps, acc, batch, st, c->L, first, outs, flags, tail, tail + 2, x->rank, x->world, epoch);
+    if (rc) return rc;
+    *result = x->local + (epoch & 1) * x->slot_words;
+    return TFB_OK;
+}
+/* 1 when a wait of an earlier push timed out (a peer never arrived); synchronises the stream's device first */
+int tfb_xchg_check(tfb_xchg* x, int* timed_out) {
+    if (!x || !timed_out) { tfb_set_error("null exchange"); return TFB_EINVAL; }
+    CHECK_CTX(x->ctx);
+    u32 e = 0;
+    TFB_CUDA(cudaDeviceSynchronize());
+    TFB_CUDA(cudaMemcpy(&e, (u32*)(x->local + 2 * x->slot_words + TFB_MAX_PEERS) + 2, sizeof(u32), cudaMemcpyDeviceToHost));
+    *timed_out = (int)e;
+    return TFB_OK;
 }
 
 // ---------------------------------------------------------- host-buffer variants

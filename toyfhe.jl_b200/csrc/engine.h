@@ -127,6 +127,12 @@ int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStrea
 int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStream_t st);   // src: v3k::NttSrc
 int launch_ntt_s_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);
 int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);   // ntt_kernels3.cu
+int launch_ntt_s_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);
+int launch_ntt_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);              // ntt_kernels3.cu
+#define TFB_MAX_PEERS 8
+int launch_ks_finish_push(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64 batch, cudaStream_t st, u32 Lct, u32 first,
+                          u64* const* outs, u64* const* flags, u32* count, u32* err, u32 rank, u32 world, u64 epoch);                 // rns_kernels.cu
+int launch_ks_limbs(tfb_ctx* c, const u64* cend, u64 ct_stride, u64* limbs, u64 batch, cudaStream_t st);                             // rns_kernels.cu
 // forward transform of `polys` polynomials of c->L rows each: rows [0, lq) of polynomial p from base0 (p < polys0) or base1,
 // rows [lq, c->L) from ext [polys][c->L - lq][N]; out contiguous.  -1: kernel family not applicable.
 int launch_ntt_gather(tfb_ctx* c, const u64* base0, const u64* base1, u32 polys0, u32 lq, const u64* ext, u64* out, u64 polys, cudaStream_t st);   // ntt_kernels3.cu

@@ -173,6 +173,27 @@ TFB_HD void pass1_crt(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3
 #pragma unroll
     for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
 }
+// Base-2^w keyswitch digits (rlwe_she.jl:331-337) formed while the row is loaded: the row in shared memory is ONE 64-bit limb
+// of the binary integers X_n (limb-major [limbs][N], ks_limbs_kernel), the digit is bits off .. off+w-1 of it; a digit that
+// straddles two limbs takes its upper bits from the next limb row with ordinary (L2) loads -- `hi` is null otherwise.
+// 2^w <= every target prime (the caller checks), so the digit is its own canonical residue.
+template <int R>
+TFB_HD void pass1_pow2(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3& rp, const u32 t, const u32 off, const u64 mask,
+                       const u64* __restrict__ hi) {
+    if (hi == nullptr) {
+#pragma unroll
+        for (int a = 0; a < 32; a++) x[a] = (smem[slot<R>(a, t)] >> off) & mask;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 32; a++) x[a] = ((smem[slot<R>(a, t)] >> off) | (hi[a * NttGeo<R>::T + t] << (64 - off))) & mask;
+    }
+    u32 tb[5];
+#pragma unroll
+    for (int s = 1; s <= 5; s++) tb[s - 1] = 1u << (s - 1);
+    levels3<5, 0x08>(x, tw, tb, rp);
+#pragma unroll
+    for (int a = 0; a < 32; a++) smem[slot<R>(a, t)] = x[a];
+}
 // pass 2 (levels 6..10): thread (a2 = t >> R, c2 = t mod RS) holds b = 0..31; bound 10 -> (reduce) 6 -> 10 -> 14 -> (reduce) 6 -> 10
 template <int R>
 TFB_HD void pass2(u64* x, u64* smem, const tw_t* __restrict__ tw, const Red3& rp, const u32 t, const u32 s0, const u32 blk) {

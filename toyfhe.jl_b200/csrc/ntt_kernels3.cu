@@ -328,3 +328,14 @@ int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* 
     if (r->logN == 14) return v3k::launch_crt<4>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
     return launch_ntt_s_crt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
 }
+
+// Base-2^w keyswitch digits formed inside the forward transform's load phase from the binary limbs of the integers
+// (N = 2^12 .. 2^14; ntt_core3.cuh pass1_pow2).  -1: not applicable.
+int launch_ntt_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    if (!r->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || g_ntt_version != 3 || r->logN < 12 || r->logN > 14) return -1;
+    if (w == 0 || w > 63) return -1;
+    for (u32 i = 0; i < r->L; i++)
+        if ((1ull << w) > r->q[i]) return -1;
+    if (r->logN == 14) return v3k::launch_pow2<4>(r, limbs, nl, w, dig, k0, dn, batch, st);
+    return launch_ntt_s_pow2(r, limbs, nl, w, dig, k0, dn, batch, st);
+}

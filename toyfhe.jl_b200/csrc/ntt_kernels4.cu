@@ -36,3 +36,9 @@ int launch_ntt_s_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64
     if (r->logN == 13) return v3k::launch_crt<3>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
     return -1;
 }
+
+int launch_ntt_s_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    if (r->logN == 12) return v3k::launch_pow2<2>(r, limbs, nl, w, dig, k0, dn, batch, st);
+    if (r->logN == 13) return v3k::launch_pow2<3>(r, limbs, nl, w, dig, k0, dn, batch, st);
+    return -1;
+}

@@ -97,21 +97,25 @@ __device__ __forceinline__ const u64* src_row(const u64* in, const NttSrc& src, 
     return src.ext + ((u64)p * (src.lj - src.lq) + (i - src.lq)) * Geo::N;
 }
 
-// CRT keyswitch digits formed inside the transform (CRT = true, s0 = 0): unit = (b * dn + kk) * L + j is digit k0 + kk of
+// CRT keyswitch digits formed inside the transform (DIG = 1, s0 = 0): unit = (b * dn + kk) * L + j is digit k0 + kk of
 // ciphertext b under target prime j; its source row is residue row k0 + kk of that ciphertext's last component.
+// Base-2^w digits (DIG = 2): `cend` is the limb-major binary form [batch][nl][N] of the integers (ct_stride = nl * N words);
+// digit k0 + kk is bits (k0 + kk) w .. of it, so its source row is limb ((k0 + kk) w) / 64 (pass1_pow2).
 struct CrtDig {
     const u64* cend;
     u64 ct_stride;
-    const PrimeParams* ppq;   // primes of the ciphertext ring (source)
+    const PrimeParams* ppq;   // primes of the ciphertext ring (source); CRT digits only
     u32 k0, dn;
+    u32 w, nl;                // base-2^w digits only
 };
-template <int R>
+template <int R, int DIG>
 __device__ __forceinline__ const u64* crt_row(const CrtDig& cd, const u32 unit, const u32 L) {
     const u32 d = unit / L;                        // (b, kk)
-    return cd.cend + (u64)(d / cd.dn) * cd.ct_stride + (u64)(cd.k0 + d % cd.dn) * NttGeo<R>::N;
+    const u32 k = cd.k0 + d % cd.dn;
+    return cd.cend + (u64)(d / cd.dn) * cd.ct_stride + (u64)(DIG == 2 ? (k * cd.w) >> 6 : k) * NttGeo<R>::N;
 }
 
-template <int R, bool S0ZERO, bool CRT = false>
+template <int R, bool S0ZERO, int DIG = 0>   // DIG: 0 rows from memory, 1 CRT digits, 2 base-2^w digits formed on load
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
                  const PrimeParams* __restrict__ pp, const u32 L, const u32 s0_, const u32 nunits, const u32 in_div,
@@ -129,13 +133,13 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    __shared__ u64 crt_q[CRT ? TFB_MAX_L : 1];   // source primes of the digits (CRT): read from shared memory, not through a dependent global load per row
-    if (CRT && t < cd.dn) crt_q[t] = cd.ppq[cd.k0 + t].pc.q;
+    __shared__ u64 crt_q[DIG == 1 ? TFB_MAX_L : 1];   // source primes of the digits (CRT): read from shared memory, not through a dependent global load per row
+    if (DIG == 1 && t < cd.dn) crt_q[t] = cd.ppq[cd.k0 + t].pc.q;
     build_redtab(redtab, pp, L, t, Geo::T);
     __syncthreads();
     // in_div > 1 (s0 = 0 only): input row = unit / in_div -- one small-integer polynomial (a keyswitch digit) is
     // transformed under in_div consecutive primes without being replicated in memory first
-    if (t < 32 && unit < nunits) tma_load_row_skewed<R>(smem, CRT ? crt_row<R>(cd, unit, L) : src_row<R>(in, src, unit, in_div, s0, nrow), &bar, t);
+    if (t < 32 && unit < nunits) tma_load_row_skewed<R>(smem, DIG ? crt_row<R, DIG>(cd, unit, L) : src_row<R>(in, src, unit, in_div, s0, nrow), &bar, t);
     u32 parity = 0;
     u64 x[32];
     for (; unit < nunits; unit += gridDim.x) {
@@ -150,15 +154,20 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         {
             const u32 nxt = unit + gridDim.x;
             if (t < 32 && nxt < nunits) {
-                const u64* p = CRT ? crt_row<R>(cd, nxt, L) : src_row<R>(in, src, nxt, in_div, s0, nrow);
+                const u64* p = DIG ? crt_row<R, DIG>(cd, nxt, L) : src_row<R>(in, src, nxt, in_div, s0, nrow);
                 l2_prefetch(p + t * Geo::T, Geo::T * 8);
                 if (t == 0) next_src = p;       // read back after pass 3's loads (three barriers later)
             }
         }
         mbar_wait(&bar, parity);
         parity ^= 1;
-        if (CRT) v3::pass1_crt<R>(x, smem, tw, rp, t, crt_q[(unit / L) % cd.dn], pp[prime].pc.br_hi);
-        else v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
+        if (DIG == 1) v3::pass1_crt<R>(x, smem, tw, rp, t, crt_q[(unit / L) % cd.dn], pp[prime].pc.br_hi);
+        else if (DIG == 2) {
+            const u32 d = unit / L, bit = (cd.k0 + d % cd.dn) * cd.w, limb = bit >> 6, off = bit & 63;
+            const bool two = off + cd.w > 64 && limb + 1 < cd.nl;
+            v3::pass1_pow2<R>(x, smem, tw, rp, t, off, (1ull << cd.w) - 1,
+                              two ? cd.cend + (u64)(d / cd.dn) * cd.ct_stride + (u64)(limb + 1) * Geo::N : nullptr);
+        } else v3::pass1<R>(x, smem, tw, rp, t, s0, blk);     // reads and writes this thread's own slots
         __syncthreads();
         v3::pass2<R>(x, smem, tw, rp, t, s0, blk);
         __syncthreads();
@@ -311,7 +320,8 @@ template <int R>
 int setup_s() {
     const int smem = (int)v3::Lay<R>::ROW_BYTES;
     TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFB_CUDA(cudaFuncSetAttribute(ntt_fwd_s_kernel<R, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv_s_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return TFB_OK;
 }
@@ -344,9 +354,26 @@ int launch_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig,
     const u64 slots = (u64)(r->num_sms > 0 ? r->num_sms : 148) * (512 / Geo::T);
     const unsigned grid = (unsigned)(rows < slots ? rows : slots);
     CrtDig cd;
-    cd.cend = cend; cd.ct_stride = ct_stride; cd.ppq = c->d_pp; cd.k0 = k0; cd.dn = dn;
+    cd.cend = cend; cd.ct_stride = ct_stride; cd.ppq = c->d_pp; cd.k0 = k0; cd.dn = dn; cd.w = 0; cd.nl = 0;
     ProfScope ps(PC_NTT_FWD, st);
-    ntt_fwd_s_kernel<R, true, true><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(nullptr, dig, r->d_fwd, r->d_pp, r->L, 0, (u32)rows, 1, NttSrc(), cd);
+    ntt_fwd_s_kernel<R, true, 1><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(nullptr, dig, r->d_fwd, r->d_pp, r->L, 0, (u32)rows, 1, NttSrc(), cd);
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
+// Base-2^w keyswitch digits k0 .. k0+dn-1 of the integers whose binary limbs are `limbs` ([batch][nl][N], ks_limbs_kernel)
+// in the NTT domain of ring r: dig [batch][dn][r->L][N].  The caller guarantees 0 < w < 64 and 2^w <= every prime of r.
+template <int R>
+int launch_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
+    typedef NttGeo<R> Geo;
+    const u64 rows = batch * dn * r->L;
+    if (rows > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
+    const u64 slots = (u64)(r->num_sms > 0 ? r->num_sms : 148) * (512 / Geo::T);
+    const unsigned grid = (unsigned)(rows < slots ? rows : slots);
+    CrtDig cd;
+    cd.cend = limbs; cd.ct_stride = (u64)nl * Geo::N; cd.ppq = nullptr; cd.k0 = k0; cd.dn = dn; cd.w = w; cd.nl = nl;
+    ProfScope ps(PC_NTT_FWD, st);
+    ntt_fwd_s_kernel<R, true, 2><<<grid, Geo::T, v3::Lay<R>::ROW_BYTES, st>>>(nullptr, dig, r->d_fwd, r->d_pp, r->L, 0, (u32)rows, 1, NttSrc(), cd);
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

@@ -742,6 +742,44 @@ __global__ void ks_digits_pow2_kernel(const u64* __restrict__ cend, const u64 ct
     }
 }
 
+// The integers X in [0,Q) themselves, as L binary limbs each, limb-major: limbs [B][L][N].  One Garner conversion per
+// coefficient, done once; the forward transform then cuts each base-2^w digit out of a limb row while it loads it
+// (ntt_core3.cuh pass1_pow2), so neither the digit rows nor the per-slice repeats of this reconstruction exist.
+__global__ void ks_limbs_kernel(const u64* __restrict__ cend, const u64 ct_stride, u64* __restrict__ limbs, const u32 L,
+                                const u32 logN, const GarnerTab g, const PrimeParams* __restrict__ ppq, const u64 total) {
+    const u32 N = 1u << logN;
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u64 b = idx >> logN;
+    const u32 n = (u32)(idx & (N - 1));
+    u64 r[MAXD], d[MAXD], X[MAXD + 1];
+    for (u32 i = 0; i < L; i++) r[i] = cend[b * ct_stride + ((u64)i << logN) + n];
+    garner_digits(r, d, L, g, ppq);
+    u32 nl = 1;
+    X[0] = d[L - 1];
+    for (int i = (int)L - 2; i >= 0; i--) {          // Horner over the mixed-radix digits, as in ks_digits_pow2_kernel
+        const u64 m = ppq[i].pc.q;
+        u64 carry = d[i];
+        for (u32 k = 0; k < nl; k++) {
+            const u64 lo = X[k] * m, hi = __umul64hi(X[k], m);
+            const u64 s = lo + carry;
+            X[k] = s;
+            carry = hi + (s < lo);
+        }
+        X[nl++] = carry;
+    }
+    for (u32 k = 0; k < L; k++) limbs[((b * L + k) << logN) + n] = X[k];
+}
+int launch_ks_limbs(tfb_ctx* c, const u64* cend, u64 ct_stride, u64* limbs, u64 batch, cudaStream_t st) {
+    if (!batch) return TFB_OK;
+    if (c->L > MAXD || !c->conv_ok) { tfb_set_error("keyswitch digits: basis too large for exact conversion"); return TFB_EUNSUPPORTED; }
+    const u64 total = batch * c->N;
+    const unsigned tb = 64;
+    { ProfScope ps(PC_KS_DIGITS, st); ks_limbs_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(cend, ct_stride, limbs, c->L, c->logN, garner_of(c), c->d_pp, total); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+
 int launch_ks_digits(tfb_ctx* c, tfb_ctx* target, int w, const u64* cend, u64 ct_stride, u64* out, u32 k0, u32 Dn,
                      u64 batch, cudaStream_t st, bool compact) {
     if (!batch || !Dn) return TFB_OK;
@@ -896,6 +934,76 @@ __global__ void ks_accum1_kernel(const u64* __restrict__ dig, const u64* __restr
     }
 }
 
+// Few coefficients (one ciphertext, or one residue shard of it): one thread per coefficient leaves the GPU nearly empty and
+// every thread walks all Dn digit rows one dependent group of loads after the other (101 us for 95 MB at N = 2^14, one
+// prime, D = 241).  Here blockDim = (32, S): warp y sums the digits kk = y, y + S, .. of 32 adjacent coefficients and the S
+// partial sums of a coefficient meet in shared memory, so S times as many loads are in flight.
+template <int S>
+__global__ void __launch_bounds__(32 * S)
+ks_accum_split_kernel(const u64* __restrict__ dig, const u64* __restrict__ key, u64* __restrict__ acc, const u32 L,
+                      const u32 logN, const u32 k0, const u32 Dn, const int accumulate, const PrimeParams* __restrict__ pp,
+                      const u32 cap) {
+    constexpr u32 U = 4;
+    __shared__ u64 part[S][2][32];
+    const u32 N = 1u << logN, x = threadIdx.x, y = threadIdx.y;
+    const u64 kstride = (u64)L << logN;
+    const u64 idx = (u64)blockIdx.x * 32 + x;      // the launch covers B L N / 32 blocks exactly (32 | N)
+    const u32 n = (u32)(idx & (N - 1));
+    const u64 r = idx >> logN;  // (b, i)
+    const u64 b = r / L;
+    const u32 i = (u32)(r % L);
+    const PrimeConst pc = pp[i].pc;
+    acc128 a1 = {0, 0}, a2 = {0, 0};
+    const u64* dp = dig + (((b * Dn) * L + i) << logN) + n;
+    const u64* kp = key + ((((u64)k0 * 2) * L + i) << logN) + n;
+    u32 pending = 0, kk = y;
+    for (; kk + (U - 1) * S < Dn; kk += U * S) {
+        if (pending + U > cap) {
+            a1.lo = red128_full(a1, pc); a1.hi = 0;
+            a2.lo = red128_full(a2, pc); a2.hi = 0;
+            pending = 0;
+        }
+        u64 p[U], km[U], kd[U];
+#pragma unroll
+        for (u32 u = 0; u < U; u++) {
+            p[u] = dp[(u64)(kk + u * S) * kstride];
+            km[u] = kp[(u64)(kk + u * S) * 2 * kstride];
+            kd[u] = kp[(u64)(kk + u * S) * 2 * kstride + kstride];
+        }
+#pragma unroll
+        for (u32 u = 0; u < U; u++) {
+            mac128(a1, kd[u], p[u]);
+            mac128(a2, km[u], p[u]);
+        }
+        pending += U;
+    }
+    for (; kk < Dn; kk += S) {
+        if (pending + 1 > cap) {
+            a1.lo = red128_full(a1, pc); a1.hi = 0;
+            a2.lo = red128_full(a2, pc); a2.hi = 0;
+            pending = 0;
+        }
+        const u64 p = dp[(u64)kk * kstride];
+        mac128(a1, kp[(u64)kk * 2 * kstride + kstride], p);
+        mac128(a2, kp[(u64)kk * 2 * kstride], p);
+        pending++;
+    }
+    part[y][0][x] = red128_full(a1, pc);
+    part[y][1][x] = red128_full(a2, pc);
+    __syncthreads();
+    if (y < 2) {                                   // warp y finishes component y of its 32 coefficients
+        u64* o = acc + (((b * 2 + y) * L + i) << logN) + n;
+        acc128 t = {accumulate ? *o : 0, 0};
+#pragma unroll
+        for (u32 s = 0; s < (u32)S; s++) {
+            const u64 v = part[s][y][x];
+            t.lo += v;
+            t.hi += t.lo < v;
+        }
+        *o = red128_full(t, pc);
+    }
+}
+
 int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, u64* acc, int accumulate, u64 batch,
                     cudaStream_t st) {
     if (!batch) return TFB_OK;
@@ -908,7 +1016,14 @@ int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, 
     const u64 total2 = batch * c->L * c->N / 2;
     const unsigned tb = 256;
     ProfScope ps(PC_KS_ACCUM, st);
-    if (total2 < 200000 || (c->N / 2) % tb != 0) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
+    const u64 total = 2 * total2;
+    // split geometry measured on B200 at N = 2^14, D = 241 (tools/exp_accum.py, profiles/r02_keyswitch_latency.txt): it pays
+    // for one ciphertext over a few primes (95 -> 23 us at one prime, 117 -> 80 us at four) and not beyond
+    if (!g_force_generic && c->N % 32 == 0 && Dn >= 64 && total <= 100000) {
+        const unsigned nb = (unsigned)(total / 32);
+        if (total <= 40000) ks_accum_split_kernel<8><<<nb, dim3(32, 8), 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, cap);
+        else ks_accum_split_kernel<4><<<nb, dim3(32, 4), 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, cap);
+    } else if (total2 < 200000 || (c->N / 2) % tb != 0) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
         ks_accum1_kernel<<<grid_for(2 * total2, tb), tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, 2 * total2, cap);
     } else {
         ks_accum_kernel<<<grid_for(total2, tb), tb, 0, st>>>((const ulonglong2*)dig, (const ulonglong2*)key, (ulonglong2*)acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total2, cap);
@@ -939,6 +1054,63 @@ __global__ void ks_finish_kernel(const u64* __restrict__ ct, const u32 comps, co
         out[idx] = v;
     }
 }
+// Sharded keyswitch epilogue fused with the exchange of the result rows (BASELINE config 4, residues sharded over GPUs):
+// the value ks_finish_kernel would write is stored straight into EVERY rank's result buffer over NVLink peer memory (this
+// rank's rows of [B][2][Lct][N]), then the last CTA to finish publishes `epoch` in every peer's flag word and waits until
+// all peers have published theirs -- when the kernel ends, this rank's buffer holds all rows.  One launch replaces
+// ks_finish + all-gather + reassembly copy.  Ordering: data stores, fence.sys, CTA counter (device atomics), fence.sys, flag
+// stores (release.sys) on the writer; acquire.sys flag loads on the reader.
+struct PeerTab {
+    u64* out[TFB_MAX_PEERS];     // rank p's result buffer of this epoch
+    u64* flag[TFB_MAX_PEERS];    // rank p's flag words [world]; word r is written by rank r only
+    u32* count;                  // local CTA counter (zero between launches)
+    u32* err;                    // local: set when the wait timed out
+    u32 rank, world;
+};
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 globaltimer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void ks_finish_push_kernel(const u64* __restrict__ ct, const u32 comps, const u64* __restrict__ acc, const u32 L,
+                                      const u32 logN, const PrimeParams* __restrict__ pp, const u64 total, const u32 Lct,
+                                      const u32 first, const PeerTab pt, const u64 epoch) {
+    const u32 N = 1u << logN;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 n = (u32)(idx & (N - 1));
+        const u64 r = idx >> logN;  // (b, k, i)
+        const u32 i = (u32)(r % L);
+        const u64 bk = r / L;
+        const u32 k = (u32)(bk & 1);
+        const u64 b = bk >> 1;
+        const u64 q = pp[i].pc.q;
+        u64 v = acc[idx];
+        if (k + 1 < comps) v = add_mod(v, ct[(((b * comps + k) * Lct + first + i) << logN) + n], q);
+        const u64 o = (((bk * Lct) + first + i) << logN) + n;
+        for (u32 p = 0; p < pt.world; p++) pt.out[p][o] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 prev = atomicAdd(pt.count, 1u);
+        if (prev == gridDim.x - 1) {                 // every CTA's stores are fenced before its increment
+            *pt.count = 0;
+            __threadfence_system();
+            for (u32 p = 0; p < pt.world; p++) st_release_sys(pt.flag[p] + pt.rank, epoch);
+            const u64 t0 = globaltimer_ns();
+            for (u32 p = 0; p < pt.world; p++)
+                while (ld_acquire_sys(pt.flag[pt.rank] + p) < epoch)
+                    if (globaltimer_ns() - t0 > 2000000000ull) { *pt.err = 1; return; }   // a peer never arrived: report, do not hang
+        }
+    }
+}
+
 struct RaiseArgs {
     tw_t pm[TFB_MAX_L];   // P mod q_i
     tw_t inv[TFB_MAX_L];  // (P mod q_i)^-1
@@ -968,6 +1140,19 @@ int launch_ks_finish(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64* 
     const u64 total = batch * 2 * c->L * c->N;
     const unsigned tb = 256, nb = grid_for(total, tb);
     { ProfScope ps(PC_KS_FINISH, st); ks_finish_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, out, c->L, c->logN, c->d_pp, total, Lct ? Lct : c->L, first); }
+    TFB_CUDA(cudaGetLastError());
+    return TFB_OK;
+}
+int launch_ks_finish_push(tfb_ctx* c, const u64* ct, u32 comps, const u64* acc, u64 batch, cudaStream_t st, u32 Lct, u32 first,
+                          u64* const* outs, u64* const* flags, u32* count, u32* err, u32 rank, u32 world, u64 epoch) {
+    if (!batch) return TFB_OK;
+    PeerTab pt;
+    for (u32 p = 0; p < world; p++) { pt.out[p] = outs[p]; pt.flag[p] = flags[p]; }
+    pt.count = count; pt.err = err; pt.rank = rank; pt.world = world;
+    const u64 total = batch * 2 * c->L * c->N;
+    const unsigned tb = 256;
+    unsigned nb = grid_for(total, tb);
+    { ProfScope ps(PC_KS_FINISH, st); ks_finish_push_kernel<<<nb, tb, 0, st>>>(ct, comps, acc, c->L, c->logN, c->d_pp, total, Lct, first, pt, epoch); }
     TFB_CUDA(cudaGetLastError());
     return TFB_OK;
 }

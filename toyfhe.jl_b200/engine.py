@@ -29,7 +29,9 @@ ABI_SYMBOLS = [
     "tfb_ntt_fwd", "tfb_ntt_inv", "tfb_add", "tfb_sub", "tfb_mul", "tfb_neg", "tfb_scalar_mul", "tfb_mul_plain", "tfb_add_plain", "tfb_lincomb",
     "tfb_ring_mul", "tfb_galois", "tfb_rescale", "tfb_crt_expand",
     "tfb_ct_tensor", "tfb_bfv_switch", "tfb_bfv_contract", "tfb_bfv_mul",
-    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
+    "tfb_keyswitch_digits", "tfb_keyswitch", "tfb_keyswitch_shard", "tfb_keyswitch_shard_push",
+    "tfb_xchg_create", "tfb_xchg_export", "tfb_xchg_attach_ipc", "tfb_xchg_attach_ptr", "tfb_xchg_local", "tfb_xchg_check", "tfb_xchg_destroy",
+    "tfb_centered_mod", "tfb_ckks_encode", "tfb_ckks_decode", "tfb_sample_uniform", "tfb_sample_gaussian", "tfb_bfv_encode", "tfb_bfv_decode", "tfb_bfv_encode_host", "tfb_bfv_decode_host",
     "tfb_ntt_fwd_host", "tfb_ntt_inv_host", "tfb_ring_mul_host", "tfb_ct_tensor_host",
     "tfb_bfv_mul_host", "tfb_rescale_host",
 ]
@@ -392,6 +394,17 @@ class Context:
                                              C.c_uint64(B), _stream_ptr(stream, self.device)))
         return out
 
+    def keyswitch_shard_push(self, shard: "Context", first: int, key_dual_shard, ct, w: int, xchg: "PeerExchange", stream=None):
+        """keyswitch_shard with the exchange fused into its last kernel: returns the WHOLE result [B][2][L][N] as a view of
+        this rank's exchange slot (valid until the call after next); every rank of the exchange makes the same call."""
+        comps = ct.shape[-3]
+        B = self._batch(ct, comps)
+        res = C.c_void_p()
+        _check(self._lib.tfb_keyswitch_shard_push(self.h, shard.h, C.c_uint32(first), C.c_uint32(w), _ptr(key_dual_shard),
+                                                  C.c_uint32(key_dual_shard.shape[0]), _ptr(ct), C.c_uint32(comps), xchg.h,
+                                                  C.byref(res), C.c_uint64(B), _stream_ptr(stream, self.device)))
+        return xchg.view(res.value, tuple(ct.shape[:-3]) + (2, self.L, self.N))
+
     # -- host-buffer entry points (numpy uint64 or pinned torch tensors)
     def ntt_fwd_host(self, a, out, stream=None):
         _check(self._lib.tfb_ntt_fwd_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._rows(a)), _stream_ptr(stream, self.device)))
@@ -428,3 +441,60 @@ class Context:
     def rescale_host(self, a, out, stream=None):
         _check(self._lib.tfb_rescale_host(self.h, _ptr(a), _ptr(out), C.c_uint64(self._polys(a)), _stream_ptr(stream, self.device)))
         return out
+
+
+class _RawDevice:
+    """a device allocation of the engine exposed to torch (torch.as_tensor reads __cuda_array_interface__)"""
+
+    def __init__(self, ptr: int, words: int):
+        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """tfb_xchg: this rank's result slots + flag words for the sharded keyswitch whose epilogue pushes its rows into every
+    rank's slot over NVLink peer memory (include/toyfhe_b200.h).  ``attach`` takes the handles of ALL ranks in rank order
+    (as torch.distributed.all_gather_object returns them); ``attach_local`` wires exchanges that live in one process."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, slot_words: int):
+        self._lib = load_library()
+        self.ctx, self.rank, self.world, self.slot_words = ctx, rank, world, int(slot_words)
+        h = C.c_void_p()
+        _check(self._lib.tfb_xchg_create(ctx.h, C.c_uint32(rank), C.c_uint32(world), C.c_uint64(8 * self.slot_words), C.byref(h)))
+        self.h = h
+        base = C.c_void_p()
+        _check(self._lib.tfb_xchg_local(self.h, C.byref(base)))
+        self.base = base.value
+        import torch
+        with torch.cuda.device(ctx.device):
+            self._slots = torch.as_tensor(_RawDevice(self.base, 2 * self.slot_words), device=f"cuda:{ctx.device}")
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _check(self._lib.tfb_xchg_export(self.h, buf))
+        return bytes(buf)
+
+    def attach(self, handles):
+        for p, hb in enumerate(handles):
+            if p != self.rank:
+                _check(self._lib.tfb_xchg_attach_ipc(self.h, C.c_uint32(p), (C.c_uint8 * 64).from_buffer_copy(hb)))
+
+    def attach_local(self, peers):
+        for p, other in enumerate(peers):
+            if p != self.rank:
+                _check(self._lib.tfb_xchg_attach_ptr(self.h, C.c_uint32(p), C.c_void_p(other.base)))
+
+    def view(self, ptr: int, shape):
+        off = (ptr - self.base) // 8
+        n = int(np.prod(shape))
+        return self._slots[off:off + n].view(*shape)
+
+    def timed_out(self) -> bool:
+        t = C.c_int()
+        _check(self._lib.tfb_xchg_check(self.h, C.byref(t)))
+        return bool(t.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._slots = None
+            _check(self._lib.tfb_xchg_destroy(self.h))
+            self.h = None

@@ -166,3 +166,23 @@ def keyswitch_residue_sharded(shard_op: Callable[[int, int], torch.Tensor], L: i
     if hi <= lo:
         raise ValueError("more ranks than RNS primes: residue sharding needs world <= L")
     return allgather_prime_rows(shard_op(lo, hi), L, group=group)
+
+
+def open_peer_exchange(ctx, L: int, max_batch: int, group=None):
+    """One PeerExchange per rank for results of up to max_batch ciphertexts ([B][2][L][N]), the IPC handles swapped with
+    all_gather_object.  Collective: every rank of the group calls it."""
+    from .engine import PeerExchange
+    rank, world = _world(group)
+    x = PeerExchange(ctx, rank, world, max_batch * 2 * L * ctx.N)
+    handles = [None] * world
+    dist.all_gather_object(handles, x.handle(), group=group)
+    x.attach(handles)
+    dist.barrier(group=group)
+    return x
+
+
+def keyswitch_residue_sharded_push(ctx, shard, lo: int, key_rows: torch.Tensor, ct: torch.Tensor, w: int, xchg) -> torch.Tensor:
+    """keyswitch_residue_sharded with the gather fused into the epilogue kernel (tfb_keyswitch_shard_push): no collective
+    call on the data path -- the rows travel as peer stores of the kernel that computes them.  [B][2][L][N] on every rank, a
+    view of the exchange slot (copy it if it has to outlive the next two calls)."""
+    return ctx.keyswitch_shard_push(shard, lo, key_rows, ct, w, xchg)
