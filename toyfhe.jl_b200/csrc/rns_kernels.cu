@@ -1017,7 +1017,7 @@ int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, 
     const unsigned tb = 256;
     ProfScope ps(PC_KS_ACCUM, st);
     const u64 total = 2 * total2;
-    // split geometry measured on B200 at N = 2^14, D = 241 (tools/exp_accum.py, profiles/r02_keyswitch_latency.txt): it pays
+    // split geometry measured on B200 at N = 2^14, D = 241 (profiles/r02_keyswitch_latency.txt): it pays
     // for one ciphertext over a few primes (95 -> 23 us at one prime, 117 -> 80 us at four) and not beyond
     if (!g_force_generic && c->N % 32 == 0 && Dn >= 64 && total <= 100000) {
         const unsigned nb = (unsigned)(total / 32);
