@@ -1,6 +1,7 @@
 """Driver for ncu captures of the keyswitch kernels: BASELINE config 4 (N=2^14, 8x60-bit primes, base-4 digits, D=241) at
 batch 1 and 8, and config 3's rotation keyswitch (N=2^15, 60+9x40+special 60, CRT digits, ModulusRaised) at batch 64.
-    python tools/prof_keyswitch.py c4 1 | c4 8 | c3 64     (prints per-class CUDA-event times as well)"""
+    python tools/prof_keyswitch.py c4 1 | c4 8 | c3 64     (prints per-class CUDA-event times as well)
+    python tools/prof_keyswitch.py c4s 1                   one-prime residue shard of config 4 (what each of 8 GPUs runs)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +17,16 @@ def rnd(qs, N, shape):
         out[..., i, :] = rng.integers(0, q, size=shape + (N,), dtype=np.uint64)
     return out
 
-if which == "c4":
+if which == "c4s":
+    N, w = 1 << 14, 2
+    qs, psis = T.prime_chain(N, [60] * 8)
+    ctx, shard = T.Context(N, qs, psis), T.Context(N, qs[:1], psis[:1])
+    D = T.ndigits(qs, w)
+    key = shard.sample_uniform(9, 1, (D, 2))
+    ct = ctx.to_device(rnd(qs, N, (B, 3)))
+    out = shard.empty((B, 2, 1, N))
+    run = lambda: ctx.keyswitch_shard(shard, 0, key, ct, w, out=out)
+elif which == "c4":
     N, w = 1 << 14, 2
     qs, psis = T.prime_chain(N, [60] * 8)
     ctx = T.Context(N, qs, psis)
