@@ -84,3 +84,40 @@ ctx.mul_plain(ct, p, out=acc, accumulate=True)
 ctx.add_plain_first(acc, p)
 torch.cuda.synchronize()
 print("CRT digits inside the transform / mul_plain / add_plain ok", flush=True)
+# ---- base-2^w digits cut out of the binary limbs inside the transform (incl. digits that straddle two limbs), the split
+# accumulate for few coefficients, lincomb, and the epilogue that pushes result rows into every rank's buffer (two ranks of
+# this process on this GPU, one stream each)
+N = 4096
+qs, psis = T.prime_chain(N, [60, 60, 60, 60])
+ctx, orc = T.Context(N, qs, psis), CO.Rns(N, qs, psis)
+for w in (2, 7):
+    D = T.ndigits(qs, w)
+    keyh = rnd(rng, qs, (D, 2), N)
+    key = ctx.ntt_fwd(ctx.to_device(keyh))
+    cth = rnd(rng, qs, (1, 3), N)
+    got = H(ctx.keyswitch(key, ctx.to_device(cth), w))
+    w1, w2 = orc.keyswitch_accum(orc.keyswitch_digits(cth[0, 2], w), keyh, cth[0, 0], cth[0, 1])
+    assert np.array_equal(got[0, 0], w1) and np.array_equal(got[0, 1], w2)
+print("digits from limbs inside the transform + split accumulate ok", flush=True)
+ranks = []
+for r in range(2):
+    c = T.Context(N, qs, psis)
+    lo, hi = S.shard_range(4, r, 2)
+    ranks.append(dict(ctx=c, lo=lo, shard=T.Context(N, qs[lo:hi], psis[lo:hi]), krows=S.key_rows_for_shard(key, lo, hi),
+                      x=T.PeerExchange(c, r, 2, 2 * 4 * N), stream=torch.cuda.Stream()))
+for rk in ranks:
+    rk["x"].attach_local([o["x"] for o in ranks])
+ctd = ctx.to_device(cth)
+for rk in ranks:
+    rk["ctx"].keyswitch_shard(rk["shard"], rk["lo"], rk["krows"], ctd, 7)       # sizes the scratch before the concurrent calls
+torch.cuda.synchronize()
+outs = []
+for rk in ranks:
+    with torch.cuda.stream(rk["stream"]):
+        outs.append(rk["ctx"].keyswitch_shard_push(rk["shard"], rk["lo"], rk["krows"], ctd, 7, rk["x"]))
+torch.cuda.synchronize()
+for rk, o in zip(ranks, outs):
+    assert not rk["x"].timed_out() and np.array_equal(H(o), got)
+for rk in ranks:
+    rk["x"].close()
+print("peer-push epilogue ok", flush=True)
