@@ -1057,7 +1057,7 @@ int launch_ks_accum(tfb_ctx* c, u32 k0, u32 Dn, const u64* dig, const u64* key, 
         const unsigned nb = (unsigned)(total / 32);
         if (total <= 40000) ks_accum_split_kernel<8><<<nb, dim3(32, 8), 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, cap);
         else ks_accum_split_kernel<4><<<nb, dim3(32, 4), 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, cap);
-    } else if (total2 < 200000 || (c->N / 2) % tb != 0) {   // small batches: one coefficient per thread keeps more loads in flight (profiles/r01_classes.txt)
+    } else if (total2 < 100000 || (c->N / 2) % tb != 0) {   // small batches: one coefficient per thread keeps more loads in flight (with the PTX mac128 the two-coefficient kernel wins from 128 K pairs on: 217 -> 175 us, profiles/r02_keyswitch_latency.txt)
         ks_accum1_kernel<<<grid_for(2 * total2, tb), tb, 0, st>>>(dig, key, acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, 2 * total2, cap);
     } else {
         ks_accum_kernel<<<grid_for(total2, tb), tb, 0, st>>>((const ulonglong2*)dig, (const ulonglong2*)key, (ulonglong2*)acc, c->L, c->logN, k0, Dn, accumulate, c->d_pp, total2, cap);
