@@ -744,3 +744,32 @@ def test_crt_digits_formed_inside_the_transform(logN, logqs, B, comps):
     finally:
         T.force_generic(0)
     assert np.array_equal(fused, plain)
+
+
+def test_empty_batches_every_device_entry_point():
+    """batch = 0 is a valid call everywhere (the reference maps over possibly empty arrays): OK, no launch, no pointer touched"""
+    import ctypes as C
+    N = 1024
+    qs, psis = T.prime_chain(N, [60, 60, 60, 60, 60])
+    cq, cb = T.Context(N, qs[:2], psis[:2]), T.Context(N, qs[2:], psis[2:])
+    lib = T.load_library()
+    z64, z32, nul = C.c_uint64(0), C.c_uint32(0), None
+    before = T.kernel_launches()
+    calls = [
+        lib.tfb_ntt_fwd(cq.h, nul, nul, z64, nul), lib.tfb_ntt_inv(cq.h, nul, nul, z64, nul),
+        lib.tfb_add(cq.h, nul, nul, nul, z64, nul), lib.tfb_sub(cq.h, nul, nul, nul, z64, nul), lib.tfb_mul(cq.h, nul, nul, nul, z64, nul),
+        lib.tfb_neg(cq.h, nul, nul, z64, nul), lib.tfb_ring_mul(cq.h, nul, nul, nul, z64, nul),
+        lib.tfb_galois(cq.h, C.c_uint64(3), nul, nul, z64, nul), lib.tfb_rescale(cq.h, nul, nul, z64, nul),
+        lib.tfb_ct_tensor(cq.h, nul, nul, nul, z64, nul),
+        lib.tfb_bfv_mul(cq.h, cb.h, C.c_uint64(65537), nul, nul, nul, z64, nul),
+        lib.tfb_keyswitch(cq.h, None, C.c_uint32(2), nul, C.c_uint32(61), nul, C.c_uint32(3), nul, z64, nul),
+        lib.tfb_keyswitch_shard(cq.h, cq.h, z32, C.c_uint32(2), nul, C.c_uint32(61), nul, C.c_uint32(3), nul, z64, nul),
+    ]
+    assert calls == [0] * len(calls), (calls, lib.tfb_last_error())
+    assert T.kernel_launches() == before
+    # the same calls with work to do and a null buffer are rejected, not dereferenced
+    one = C.c_uint64(2)
+    assert lib.tfb_ntt_fwd(cq.h, nul, nul, one, nul) == 1
+    assert lib.tfb_ct_tensor(cq.h, nul, nul, nul, C.c_uint64(1), nul) == 1
+    assert lib.tfb_keyswitch(cq.h, None, C.c_uint32(2), nul, C.c_uint32(61), nul, C.c_uint32(3), nul, C.c_uint64(1), nul) == 1
+    assert lib.tfb_bfv_mul(cq.h, cb.h, C.c_uint64(65537), nul, nul, nul, C.c_uint64(1), nul) == 1
