@@ -211,6 +211,73 @@ TFB_D u64 red126_sp60(const u64 z1, const u64 z0, const u64 q, const u32 e) {
 #endif
 }
 
+// (hi:lo) += x y  and  (hi:lo) = x y  for x, y < 2^62 (residues and residue-sized constants: every modulus is below 2^62).
+// With 30-bit upper halves the two cross products add up in 64 bits without a carry, so the 128-bit product is four
+// 32x32->64 multiplies (one of them a multiply-add) and the accumulation seven 32-bit adds; the compiler's mul.lo + mul.hi
+// pair computes the low partial products twice (about 24 vs 16 cycles of the integer-multiply pipe per product).
+TFB_D void mac_wide62(u64& lo, u64& hi, const u64 x, const u64 y) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t"
+        ".reg .u32 x0, x1, y0, y1, l0, l1, m0, m1, h0, h1, a0, a1, a2, a3;\n\t"
+        ".reg .u64 l, m, h;\n\t"
+        "mov.b64 {x0, x1}, %2;\n\t"
+        "mov.b64 {y0, y1}, %3;\n\t"
+        "mov.b64 {a0, a1}, %0;\n\t"
+        "mov.b64 {a2, a3}, %1;\n\t"
+        "mul.wide.u32 l, x0, y0;\n\t"
+        "mul.wide.u32 m, x0, y1;\n\t"
+        "mad.wide.u32 m, x1, y0, m;\n\t"
+        "mul.wide.u32 h, x1, y1;\n\t"
+        "mov.b64 {l0, l1}, l;\n\t"
+        "mov.b64 {m0, m1}, m;\n\t"
+        "mov.b64 {h0, h1}, h;\n\t"
+        "add.cc.u32 a0, a0, l0;\n\t"
+        "addc.cc.u32 a1, a1, l1;\n\t"
+        "addc.cc.u32 a2, a2, h0;\n\t"
+        "addc.u32 a3, a3, h1;\n\t"
+        "add.cc.u32 a1, a1, m0;\n\t"
+        "addc.cc.u32 a2, a2, m1;\n\t"
+        "addc.u32 a3, a3, 0;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "mov.b64 %1, {a2, a3};\n\t"
+        "}"
+        : "+l"(lo), "+l"(hi)
+        : "l"(x), "l"(y));
+#else
+    const u128 z = (((u128)hi << 64) | lo) + (u128)x * y;
+    lo = (u64)z;
+    hi = (u64)(z >> 64);
+#endif
+}
+TFB_D void mul_wide62(u64& lo, u64& hi, const u64 x, const u64 y) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t"
+        ".reg .u32 x0, x1, y0, y1, l0, l1, m0, m1, h0, h1;\n\t"
+        ".reg .u64 l, m, h;\n\t"
+        "mov.b64 {x0, x1}, %2;\n\t"
+        "mov.b64 {y0, y1}, %3;\n\t"
+        "mul.wide.u32 l, x0, y0;\n\t"
+        "mul.wide.u32 m, x0, y1;\n\t"
+        "mad.wide.u32 m, x1, y0, m;\n\t"
+        "mul.wide.u32 h, x1, y1;\n\t"
+        "mov.b64 {l0, l1}, l;\n\t"
+        "mov.b64 {m0, m1}, m;\n\t"
+        "mov.b64 {h0, h1}, h;\n\t"
+        "add.cc.u32 l1, l1, m0;\n\t"
+        "addc.cc.u32 h0, h0, m1;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "mov.b64 %1, {h0, h1};\n\t"
+        "}"
+        : "=l"(lo), "=l"(hi)
+        : "l"(x), "l"(y));
+#else
+    const u128 z = (u128)x * y;
+    lo = (u64)z;
+    hi = (u64)(z >> 64);
+#endif
+}
+
 TFB_D u64 add_mod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 TFB_D u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 TFB_D u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }

@@ -25,9 +25,7 @@ bool g_force_generic = false;
 struct acc128 {
     u64 lo, hi;
 };
-// a += x * y for x, y < 2^62 (residues: every modulus is below 2^62).  With 30-bit upper halves the two cross products
-// add up in 64 bits without a carry, so the product is four 32x32->64 multiplies (one of them a multiply-add) and the
-// 128-bit accumulation seven 32-bit adds -- the compiler's mul.lo + mul.hi form computes the low partial products twice.
+// a += x * y for residues x, y (mac_wide62, modarith.cuh).
 // Measured (profiles/r02_keyswitch_latency.txt): -14 % on the two-coefficient accumulate at large batches (C3: 0.76 -> 0.66
 // ms), -10 % on the MNIST linear combinations; the one-coefficient kernels that keep 24 loads in flight per thread are
 // faster with the compiler's form (mac128_plain), which ptxas interleaves with the loads more freely.
@@ -36,34 +34,7 @@ __device__ __forceinline__ void mac128_plain(acc128& a, u64 x, u64 y) {
     a.lo += lo;
     a.hi += hi + (a.lo < lo);
 }
-__device__ __forceinline__ void mac128(acc128& a, u64 x, u64 y) {
-    asm("{\n\t"
-        ".reg .u32 x0, x1, y0, y1, l0, l1, m0, m1, h0, h1, a0, a1, a2, a3;\n\t"
-        ".reg .u64 l, m, h;\n\t"
-        "mov.b64 {x0, x1}, %2;\n\t"
-        "mov.b64 {y0, y1}, %3;\n\t"
-        "mov.b64 {a0, a1}, %0;\n\t"
-        "mov.b64 {a2, a3}, %1;\n\t"
-        "mul.wide.u32 l, x0, y0;\n\t"
-        "mul.wide.u32 m, x0, y1;\n\t"
-        "mad.wide.u32 m, x1, y0, m;\n\t"
-        "mul.wide.u32 h, x1, y1;\n\t"
-        "mov.b64 {l0, l1}, l;\n\t"
-        "mov.b64 {m0, m1}, m;\n\t"
-        "mov.b64 {h0, h1}, h;\n\t"
-        "add.cc.u32 a0, a0, l0;\n\t"
-        "addc.cc.u32 a1, a1, l1;\n\t"
-        "addc.cc.u32 a2, a2, h0;\n\t"
-        "addc.u32 a3, a3, h1;\n\t"
-        "add.cc.u32 a1, a1, m0;\n\t"
-        "addc.cc.u32 a2, a2, m1;\n\t"
-        "addc.u32 a3, a3, 0;\n\t"
-        "mov.b64 %0, {a0, a1};\n\t"
-        "mov.b64 %1, {a2, a3};\n\t"
-        "}"
-        : "+l"(a.lo), "+l"(a.hi)
-        : "l"(x), "l"(y));
-}
+__device__ __forceinline__ void mac128(acc128& a, u64 x, u64 y) { mac_wide62(a.lo, a.hi, x, y); }   // modarith.cuh
 // full reduction of a 128-bit value modulo q (any size of z)
 __device__ __forceinline__ u64 red128_full(acc128 a, const PrimeConst& pc) {
     return red128_any(a.hi, a.lo, pc);
