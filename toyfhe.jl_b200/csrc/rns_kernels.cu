@@ -64,7 +64,7 @@ __global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2*
             r.x = barrett_mul(x.x, y.x, pc);
             r.y = barrett_mul(x.y, y.y, pc);
         }
-        out[idx] = r;
+        out[idx] = res;
     }
 }
 
@@ -76,7 +76,7 @@ __global__ void neg_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restr
         ulonglong2 r;
         r.x = neg_mod(x.x, q);
         r.y = neg_mod(x.y, q);
-        out[idx] = r;
+        out[idx] = res;
     }
 }
 
@@ -95,7 +95,7 @@ __global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* 
         ulonglong2 r;
         r.x = shoup_full(x.x, s.w, s.wp, q);
         r.y = shoup_full(x.y, s.w, s.wp, q);
-        out[idx] = r;
+        out[idx] = res;
     }
 }
 
@@ -125,7 +125,7 @@ __global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
             r.x = add_mod(r.x, o.x, pc.q);
             r.y = add_mod(r.y, o.y, pc.q);
         }
-        out[idx] = r;
+        out[idx] = res;
     }
 }
 
@@ -1117,7 +1117,6 @@ __global__ void ks_finish_push_kernel(const u64* __restrict__ ct, const u32 comp
 }
 
 struct RaiseArgs {
-    tw_t pm[TFB_MAX_L];   // P mod q_i
     tw_t inv[TFB_MAX_L];  // (P mod q_i)^-1
 };
 __global__ void ks_finish_raised_kernel(const u64* __restrict__ ct, const u32 comps, const u64* __restrict__ acc,
@@ -1132,11 +1131,12 @@ __global__ void ks_finish_raised_kernel(const u64* __restrict__ ct, const u32 co
         const u32 k = (u32)(bk & 1);
         const u64 b = bk >> 1;
         const PrimeConst pc = pp[i].pc;
-        u64 v = acc[((bk * (l + 1) + i) << logN) + n];
-        if (k + 1 < comps)
-            v = add_mod(v, shoup_full(ct[(((b * comps + k) * l + i) << logN) + n], ra.pm[i].w, ra.pm[i].wp, pc.q), pc.q);
+        const u64 v = acc[((bk * (l + 1) + i) << logN) + n];
         const u64 sp = barrett_red64(acc[((bk * (l + 1) + l) << logN) + n], pc);  // special-prime row, un-centred
-        out[idx] = shoup_full(sub_mod(v, sp, pc.q), ra.inv[i].w, ra.inv[i].wp, pc.q);
+        // modswitch(P ct + acc) = (P ct_i + acc_i - sp) P^-1 = ct_i + (acc_i - sp) P^-1 (mod q_i): one product, not two
+        u64 res = shoup_full(sub_mod(v, sp, pc.q), ra.inv[i].w, ra.inv[i].wp, pc.q);
+        if (k + 1 < comps) res = add_mod(res, ct[(((b * comps + k) * l + i) << logN) + n], pc.q);
+        out[idx] = res;
     }
 }
 
@@ -1168,7 +1168,6 @@ int launch_ks_finish_raised(tfb_ctx* c, tfb_ctx* ext, const u64* ct, u32 comps, 
     RaiseArgs ra;
     for (u32 i = 0; i < c->L; i++) {
         if (P % c->q[i] == 0) { tfb_set_error("special prime must differ from the ciphertext primes"); return TFB_EINVAL; }
-        ra.pm[i] = h_tw(P % c->q[i], c->q[i]);
         ra.inv[i] = h_tw(h_invmod(P % c->q[i], c->q[i]), c->q[i]);
     }
     const u64 total = batch * 2 * c->L * c->N;
