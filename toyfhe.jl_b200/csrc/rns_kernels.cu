@@ -64,7 +64,7 @@ __global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2*
             r.x = barrett_mul(x.x, y.x, pc);
             r.y = barrett_mul(x.y, y.y, pc);
         }
-        out[idx] = res;
+        out[idx] = r;
     }
 }
 
@@ -76,7 +76,7 @@ __global__ void neg_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restr
         ulonglong2 r;
         r.x = neg_mod(x.x, q);
         r.y = neg_mod(x.y, q);
-        out[idx] = res;
+        out[idx] = r;
     }
 }
 
@@ -95,7 +95,7 @@ __global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* 
         ulonglong2 r;
         r.x = shoup_full(x.x, s.w, s.wp, q);
         r.y = shoup_full(x.y, s.w, s.wp, q);
-        out[idx] = res;
+        out[idx] = r;
     }
 }
 
@@ -125,7 +125,7 @@ __global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
             r.x = add_mod(r.x, o.x, pc.q);
             r.y = add_mod(r.y, o.y, pc.q);
         }
-        out[idx] = res;
+        out[idx] = r;
     }
 }
 
