@@ -127,7 +127,6 @@ int launch_ntt_s_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStrea
 int launch_ntt_s_gather(tfb_ctx* c, const void* src, u64* out, u64 rows, cudaStream_t st);   // src: v3k::NttSrc
 int launch_ntt_s_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);
 int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);   // ntt_kernels3.cu
-int launch_ntt_x_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);     // ntt_kernels3.cu
 int launch_ntt_s_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);
 int launch_ntt_pow2(tfb_ctx* r, const u64* limbs, u32 nl, u32 w, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st);              // ntt_kernels3.cu
 #define TFB_MAX_PEERS 8
@@ -141,7 +140,5 @@ int launch_ntt_bcast(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_
 int launch_ntt_inv_sub(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
 int launch_ntt_fwd_cross(tfb_ctx* c, const u64* in, u64* out, u64 rows, u32 s0, cudaStream_t st);   // ntt_kernels3.cu
 extern bool g_ntt_force_harvey;
-extern bool g_force_generic;   // rns_kernels.cu: testing hook, plain routes instead of the fused / specialised ones
-extern bool g_ntt_cross;       // ntt_kernels.cu: last global level applied on load (default on)
 extern int g_ntt_max_mode;  // debug cap on the ladder mode (2 = no cap)
 extern int g_ntt_version;  // 1 = one CTA per row (ntt_core.cuh), 3 = persistent third-generation kernels (default)

@@ -300,41 +300,6 @@ TFB_HD void pass1_cross_global(u64* x, const u64* __restrict__ even, const u64* 
         x[a] = rank ? X - tt + rp.q4 : X + tt;
     }
 }
-// The same for CRT keyswitch digits (rlwe_she.jl:326-329): `even` / `odd` are the two halves of residue row k of the
-// ciphertext (modulus qk); both operands are the centred residue re-embedded under the target prime p = rp.q (as in
-// pass1_crt) before the cross butterfly -- neither the digit rows nor their first global level ever touch HBM.
-template <int R>
-TFB_HD void pass1_cross_global_crt(u64* x, const u64* __restrict__ even, const u64* __restrict__ odd, const u32 rank, const tw_t wc,
-                                   const Red3& rp, const u32 t, const u64 qk, const u64 br_hi) {
-    const u64 hq = qk >> 1, p = rp.q;
-    if (hq < p) {
-        const u64 d = p - qk;                          // modulo 2^64
-#pragma unroll
-        for (int a = 0; a < 32; a++) {
-            const u64 cx = even[a * NttGeo<R>::T + t], cy = odd[a * NttGeo<R>::T + t];
-            const u64 X = cx > hq ? cx + d : cx, Y = cy > hq ? cy + d : cy;
-            const u64 tt = shoup_lazy4(Y, wc.w, wc.wp, rp.q, rp.ne, rp.shb);
-            x[a] = rank ? X - tt + rp.q4 : X + tt;
-        }
-    } else {
-#pragma unroll 4
-        for (int a = 0; a < 32; a++) {
-            u64 e[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const u64 c = h ? odd[a * NttGeo<R>::T + t] : even[a * NttGeo<R>::T + t];
-                const bool neg = c > hq;
-                const u64 v = neg ? qk - c : c;
-                u64 r = v - mulhi64(v, br_hi) * p;          // [0, 3p)
-                r = csub(r, 2 * p);
-                r = csub(r, p);
-                e[h] = (neg && r) ? p - r : r;
-            }
-            const u64 tt = shoup_lazy4(e[1], wc.w, wc.wp, rp.q, rp.ne, rp.shb);
-            x[a] = rank ? e[0] - tt + rp.q4 : e[0] + tt;
-        }
-    }
-}
 TFB_HD void pass1_cross_levels(u64* x, const tw_t* __restrict__ tw, const Red3& rp, const u32 s0, const u32 blk) {
     u32 tb[5];
 #pragma unroll

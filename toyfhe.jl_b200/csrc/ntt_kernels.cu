@@ -315,10 +315,6 @@ __global__ void ks_crt_stage1_kernel(const u64* __restrict__ cend, const u64 ct_
 int launch_ks_crt_ntt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 Dn, u64 batch, cudaStream_t st) {
     if (r->logN != 15 || c->N != r->N || g_ntt_version != 3 || !r->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2) return -1;
     if (k0 + Dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
-    if (!g_force_generic) {   // both the embedding and the global level inside the sub-block kernel's loads
-        const int rx = launch_ntt_x_crt(c, r, cend, ct_stride, dig, k0, Dn, batch, st);
-        if (rx != -1) return rx;
-    }
     const u64 rows = batch * Dn * r->L;
     int rc = ws_reserve(r, (size_t)rows * r->N * sizeof(u64));
     if (rc) return rc;

@@ -218,7 +218,6 @@ int ntt3_setup_device() {
     TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_s_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(ntt_inv14p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
-    TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_fwd_x_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     TFB_CUDA(cudaFuncSetAttribute(v3k::ntt_inv_sub_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::Lay<4>::ROW_BYTES));
     int rc = v3k::setup_s<4>();
     if (rc) return rc;
@@ -328,24 +327,6 @@ int launch_ntt_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* 
     if (k0 + dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
     if (r->logN == 14) return v3k::launch_crt<4>(c, r, cend, ct_stride, dig, k0, dn, batch, st);
     return launch_ntt_s_crt(c, r, cend, ct_stride, dig, k0, dn, batch, st);
-}
-
-// CRT keyswitch digits of 2^15-position rows: the centred re-embedding AND the row's one global level happen while the
-// 2^14 sub-block kernel loads its operands from the ciphertext's residue row (v3::pass1_cross_global_crt) -- no digit rows,
-// no level-1 pass through HBM.  dig [batch][dn][r->L][N] in the NTT domain.  -1: not applicable.
-int launch_ntt_x_crt(tfb_ctx* c, tfb_ctx* r, const u64* cend, u64 ct_stride, u64* dig, u32 k0, u32 dn, u64 batch, cudaStream_t st) {
-    if (!r->v3_ok || g_ntt_force_harvey || g_ntt_max_mode < 2 || g_ntt_version != 3 || !g_ntt_cross || r->logN != 15 || c->N != r->N) return -1;
-    if (k0 + dn > c->L) { tfb_set_error("keyswitch digits: digit range out of bounds"); return TFB_EINVAL; }
-    const u64 units = (batch * dn * r->L) << 1;
-    if (units > 0x7fffffffull) { tfb_set_error("too many rows for one launch"); return TFB_EINVAL; }
-    const u64 nsm = (u64)(r->num_sms > 0 ? r->num_sms : 148);
-    const unsigned grid = (unsigned)(units < nsm ? units : nsm);
-    v3k::CrtDig cd;
-    cd.cend = cend; cd.ct_stride = ct_stride; cd.ppq = c->d_pp; cd.k0 = k0; cd.dn = dn; cd.w = 0; cd.nl = 0;
-    ProfScope ps(PC_NTT_FWD, st);
-    v3k::ntt_fwd_x_kernel<4, 1><<<grid, Geo::T, v3::Lay<4>::ROW_BYTES, st>>>(nullptr, dig, r->d_fwd, r->d_pp, r->L, 1, (u32)units, cd);
-    TFB_CUDA(cudaGetLastError());
-    return TFB_OK;
 }
 
 // Base-2^w keyswitch digits formed inside the forward transform's load phase from the binary limbs of the integers

@@ -184,19 +184,15 @@ ntt_fwd_s_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
 // pair read both sub-blocks (the second read is an L2 hit), so the separate HBM pass of that level -- 27 % of the
 // N = 2^15 forward transform -- disappears at the price of one more product per position.  OUT OF PLACE only: a CTA
 // writes natural-order outputs all over the row while its partner may still be reading the inputs.
-// DIG = 1 (s0 = 1 only): row = (b * dn + kk) * L + j is CRT keyswitch digit k0 + kk of ciphertext b under target prime j; its
-// operands are the two halves of residue row k0 + kk of the ciphertext's last component (pass1_cross_global_crt).
-template <int R, int DIG = 0>
+template <int R>
 __global__ void __launch_bounds__(NttGeo<R>::T, 512 / NttGeo<R>::T)
 ntt_fwd_x_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* __restrict__ tw_all,
-                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0, const u32 nunits, const CrtDig cd = CrtDig()) {
+                 const PrimeParams* __restrict__ pp, const u32 L, const u32 s0, const u32 nunits) {
     typedef NttGeo<R> Geo;
     extern __shared__ __align__(128) u64 smem[];
     __shared__ v3::redent_t redtab[TFB_MAX_L * 16];
-    __shared__ u64 crt_q[DIG == 1 ? TFB_MAX_L : 1];
     u32 t = threadIdx.x;
     const u64 nrow = (u64)Geo::N << s0;
-    if (DIG == 1 && t < cd.dn) crt_q[t] = cd.ppq[cd.k0 + t].pc.q;
     build_redtab(redtab, pp, L, t, Geo::T);
     __syncthreads();
     u64 x[32];
@@ -207,11 +203,6 @@ ntt_fwd_x_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
         const tw_t* tw = tw_all + (u64)prime * nrow;
         const v3::Red3 rp = v3::make_red3(pp[prime].pc.q, pp[prime].sh, redtab + prime * 16);
         asm volatile("" : "+r"(t));   // see ntt_fwd_s_kernel
-        if (DIG == 1) {   // the source rows are the few residue rows of the ciphertexts: L2-resident, no prefetch
-            const u32 d = (u32)(row / L);
-            const u64* even = cd.cend + (u64)(d / cd.dn) * cd.ct_stride + (u64)(cd.k0 + d % cd.dn) * nrow;
-            v3::pass1_cross_global_crt<R>(x, even, even + Geo::N, blk & 1, tw[1], rp, t, crt_q[d % cd.dn], pp[prime].pc.br_hi);
-        } else {
         const u64* even = in + row * nrow + (u64)(blk & ~1u) * Geo::N;
         {   // the pair this CTA handles next: DRAM -> L2 while this one is transformed
             const u32 nxt = unit + gridDim.x;
@@ -219,7 +210,6 @@ ntt_fwd_x_kernel(const u64* __restrict__ in, u64* __restrict__ out, const tw_t* 
                 l2_prefetch(in + (u64)(nxt >> s0) * nrow + (u64)((nxt & ((1u << s0) - 1)) & ~1u) * Geo::N + (u64)t * Geo::T, Geo::T * 8);
         }
         v3::pass1_cross_global<R>(x, even, even + Geo::N, blk & 1, tw[(1u << (s0 - 1)) + (blk >> 1)], rp, t);
-        }
         v3::pass1_cross_levels(x, tw, rp, s0, blk);
         v3::pass1_store<R>(x, smem, t);
         __syncthreads();
