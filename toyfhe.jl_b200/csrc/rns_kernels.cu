@@ -326,6 +326,28 @@ __global__ void galois_kernel(const u64* __restrict__ in, u64* __restrict__ out,
     }
 }
 
+// Rows of 2^10 .. 2^14 positions: the gather above reads one word out of every 32-byte sector it touches (stride g^-1), so
+// the L2 -> SM traffic is four times the row; here a CTA brings its row into shared memory with full-width loads and
+// gathers there (an odd word stride is bank-conflict-free for 64-bit accesses), then writes coalesced.
+__global__ void __launch_bounds__(512) galois_row_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
+                                                         const u32 L, const u32 logN, const u32 ginv, const u64 rows) {
+    extern __shared__ __align__(16) u64 srow[];
+    const u32 N = 1u << logN;
+    for (u64 row = blockIdx.x; row < rows; row += gridDim.x) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(in + (row << logN));
+        for (u32 j = threadIdx.x; j < N / 2; j += blockDim.x) reinterpret_cast<ulonglong2*>(srow)[j] = src[j];
+        __syncthreads();
+        const u64 q = pp[row % L].pc.q;
+        u64* dst = out + (row << logN);
+        for (u32 r = threadIdx.x; r < N; r += blockDim.x) {
+            const u32 i = (ginv * r) & (2 * N - 1);
+            const u64 v = srow[i & (N - 1)];
+            dst[r] = i < N ? v : neg_mod(v, q);
+        }
+        __syncthreads();
+    }
+}
+
 int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStream_t st) {
     if (!rows) return TFB_OK;
     if (in == out) { tfb_set_error("tfb_galois cannot run in place"); return TFB_EINVAL; }
@@ -337,6 +359,20 @@ int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStre
     for (int i = 0; i < 6; i++) x = x * (2 - g * x);
     const u32 ginv = (u32)(x & (twoN - 1));
     const u64 total = rows * c->N;
+    if (!g_force_generic && c->logN >= 10 && c->logN <= 14) {
+        const size_t smem = (size_t)c->N * sizeof(u64);
+        static bool attr_done[64] = {};                      // per device (set once; harmless if two threads race to set it)
+        if (c->device >= 0 && c->device < 64 && !attr_done[c->device]) {
+            TFB_CUDA(cudaFuncSetAttribute(galois_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            attr_done[c->device] = true;
+        }
+        const u64 per_sm = smem <= 32 * 1024 ? 4 : (smem <= 64 * 1024 ? 3 : 1);
+        const u64 slots = (u64)(c->num_sms > 0 ? c->num_sms : 148) * per_sm;
+        const unsigned nb = (unsigned)(rows < slots ? rows : slots);
+        { ProfScope ps(PC_LEVEL, st); galois_row_kernel<<<nb, 512, smem, st>>>(in, out, c->d_pp, c->L, c->logN, ginv, rows); }
+        TFB_CUDA(cudaGetLastError());
+        return TFB_OK;
+    }
     const unsigned tb = 256, nb = grid_for(total, tb);
     { ProfScope ps(PC_LEVEL, st); galois_kernel<<<nb, tb, 0, st>>>(in, out, c->d_pp, c->L, c->logN, ginv, total); }
     TFB_CUDA(cudaGetLastError());
