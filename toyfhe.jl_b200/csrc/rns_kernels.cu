@@ -40,14 +40,40 @@ __device__ __forceinline__ u64 red128_full(acc128 a, const PrimeConst& pc) {
     return red128_any(a.hi, a.lo, pc);
 }
 
+// (r / d, r % d) for a small divisor d that is loop-invariant in the caller (a number of primes, of digits): the
+// reciprocal M = ceil(2^32 / d) is computed once per thread, after which a row index below 2^23 (always, in practice) costs
+// one 32-bit high multiply instead of the 64-bit division routine -- the elementwise kernels below spent most of their
+// instructions there (ks_finish_raised: 180 per word, add_plain: 175 per pair of words; profiles/r02_workloads.txt).
+// Exact for d <= 2^9 and r < 2^23: with M d = 2^32 + e, e < d, the error r e / (d 2^32) stays below 1 / d.
+struct SmallDiv {
+    u32 d, M;
+    __device__ __forceinline__ explicit SmallDiv(const u32 d_) : d(d_), M(d_ > 1 ? (u32)((0x100000000ull + d_ - 1) / d_) : 0) {}
+    __device__ __forceinline__ u64 divmod(const u64 r, u32& rem) const {
+        if (r < (1ull << 23) && d <= 512) {
+            const u32 r32 = (u32)r, q = M ? __umulhi(r32, M) : r32;
+            rem = r32 - q * d;
+            return q;
+        }
+        const u64 q = r / d;
+        rem = (u32)(r - q * d);
+        return q;
+    }
+    __device__ __forceinline__ u32 mod(const u64 r) const {
+        u32 rem;
+        divmod(r, rem);
+        return rem;
+    }
+};
+
 // ------------------------------------------------------------- elementwise
 template <int OP>
 __global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ b,
                              ulonglong2* __restrict__ out, const PrimeParams* __restrict__ pp, const u32 L,
                              const u32 logN, const u64 total2) {
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
         const u64 row = idx >> (logN - 1);
-        const PrimeConst pc = pp[row % L].pc;
+        const PrimeConst pc = pp[dl.mod(row)].pc;
         const ulonglong2 x = a[idx], y = b[idx];
         ulonglong2 r;
         if (OP == 0) {
@@ -70,8 +96,9 @@ __global__ void binop_kernel(const ulonglong2* __restrict__ a, const ulonglong2*
 
 __global__ void neg_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restrict__ out,
                            const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total2) {
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
-        const u64 q = pp[(idx >> (logN - 1)) % L].pc.q;
+        const u64 q = pp[dl.mod(idx >> (logN - 1))].pc.q;
         const ulonglong2 x = a[idx];
         ulonglong2 r;
         r.x = neg_mod(x.x, q);
@@ -87,8 +114,9 @@ struct ScalarArgs {
 __global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* __restrict__ out,
                                   const PrimeParams* __restrict__ pp, const ScalarArgs sa, const u32 L,
                                   const u32 logN, const u64 total2) {
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
-        const u32 prime = (u32)((idx >> (logN - 1)) % L);
+        const u32 prime = dl.mod(idx >> (logN - 1));
         const u64 q = pp[prime].pc.q;
         const tw_t s = sa.s[prime];
         const ulonglong2 x = a[idx];
@@ -106,10 +134,12 @@ __global__ void scalar_mul_kernel(const ulonglong2* __restrict__ a, ulonglong2* 
 template <bool ACC, bool SP>
 __global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ plain, ulonglong2* __restrict__ out,
                                  const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total2) {
-    const u64 poly2 = (u64)L << (logN - 1);
+    const SmallDiv dl(L);
+    const u64 low = (1ull << (logN - 1)) - 1;
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
-        const u64 within = idx % poly2;
-        const PrimeConst pc = pp[within >> (logN - 1)].pc;
+        const u32 prime = dl.mod(idx >> (logN - 1));
+        const u64 within = ((u64)prime << (logN - 1)) | (idx & low);
+        const PrimeConst pc = pp[prime].pc;
         const ulonglong2 x = a[idx], y = plain[within];
         ulonglong2 r;
         if (SP) {
@@ -134,10 +164,13 @@ __global__ void mul_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
 // of the first ciphertext and the stride is the ciphertext size.  In place allowed.
 __global__ void add_plain_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ plain, ulonglong2* __restrict__ out,
                                  const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 stride2, const u64 total2) {
-    const u64 poly2 = (u64)L << (logN - 1);
+    const SmallDiv dl(L);
+    const u64 low = (1ull << (logN - 1)) - 1;
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (u64)gridDim.x * blockDim.x) {
-        const u64 p = idx / poly2, within = idx - p * poly2;
-        const u64 q = pp[within >> (logN - 1)].pc.q;
+        u32 prime;
+        const u64 p = dl.divmod(idx >> (logN - 1), prime);
+        const u64 within = ((u64)prime << (logN - 1)) | (idx & low);
+        const u64 q = pp[prime].pc.q;
         const ulonglong2 x = a[p * stride2 + within], y = plain[within];
         ulonglong2 r;
         r.x = add_mod(x.x, y.x, q);
@@ -155,8 +188,9 @@ __global__ void add_plain_kernel(const ulonglong2* __restrict__ a, const ulonglo
 template <int C>
 __global__ void lincomb_kernel(const u64* __restrict__ in, const u64 in_stride, const u32 J, const u64* __restrict__ w, u64* __restrict__ out,
                                const PrimeParams* __restrict__ pp, const u32 L, const u32 logN, const u64 total) {
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
-        const u32 prime = (u32)((idx >> logN) % L);
+        const u32 prime = dl.mod(idx >> logN);
         acc128 a[C];
 #pragma unroll
         for (int c = 0; c < C; c++) a[c] = {0, 0};
@@ -316,10 +350,11 @@ int launch_tensor_dual(tfb_ctx* c, const u64* a, const u64* b, u64* out, u64 bat
 __global__ void galois_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
                               const u32 L, const u32 logN, const u32 ginv, const u64 total) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u64 row = idx >> logN;
         const u32 r = (u32)(idx & (N - 1));
-        const u64 q = pp[row % L].pc.q;
+        const u64 q = pp[dl.mod(row)].pc.q;
         const u32 i = (u32)(((u64)ginv * r) & (2 * N - 1));
         const u64 v = in[(row << logN) + (i & (N - 1))];
         out[idx] = i < N ? v : neg_mod(v, q);
@@ -384,11 +419,12 @@ int launch_galois(tfb_ctx* c, u64 g, const u64* in, u64* out, u64 rows, cudaStre
 __global__ void rescale_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
                                const ScalarArgs inv, const u32 L, const u32 logN, const u64 total) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(L - 1);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (poly, i) with i < L-1
-        const u64 p = r / (L - 1);
-        const u32 i = (u32)(r % (L - 1));
+        u32 i;
+        const u64 p = dl.divmod(r, i);
         const PrimeConst pc = pp[i].pc;
         const u64 ci = in[((p * L + i) << logN) + n];
         const u64 cl = barrett_red64(in[((p * L + (L - 1)) << logN) + n], pc);
@@ -416,11 +452,12 @@ int launch_rescale(tfb_ctx* c, const u64* in, u64* out, u64 polys, cudaStream_t 
 __global__ void crt_expand_kernel(const u64* __restrict__ in, u64* __restrict__ out, const PrimeParams* __restrict__ pp,
                                   const ScalarArgs pm, const u32 L, const u32 logN, const u64 total) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(L + 1);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (poly, i) with i <= L
-        const u64 p = r / (L + 1);
-        const u32 i = (u32)(r % (L + 1));
+        u32 i;
+        const u64 p = dl.divmod(r, i);
         u64 v = 0;
         if (i < L) v = shoup_full(in[((p * L + i) << logN) + n], pm.s[i].w, pm.s[i].wp, pp[i].pc.q);
         out[idx] = v;
@@ -1082,11 +1119,12 @@ __global__ void ks_finish_kernel(const u64* __restrict__ ct, const u32 comps, co
                                  u64* __restrict__ out, const u32 L, const u32 logN,
                                  const PrimeParams* __restrict__ pp, const u64 total, const u32 Lct, const u32 first) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (b, k, i)
-        const u32 i = (u32)(r % L);
-        const u64 bk = r / L;
+        u32 i;
+        const u64 bk = dl.divmod(r, i);
         const u32 k = (u32)(bk & 1);
         const u64 b = bk >> 1;
         const u64 q = pp[i].pc.q;
@@ -1123,11 +1161,12 @@ __global__ void ks_finish_push_kernel(const u64* __restrict__ ct, const u32 comp
                                       const u32 logN, const PrimeParams* __restrict__ pp, const u64 total, const u32 Lct,
                                       const u32 first, const PeerTab pt, const u64 epoch) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(L);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (b, k, i)
-        const u32 i = (u32)(r % L);
-        const u64 bk = r / L;
+        u32 i;
+        const u64 bk = dl.divmod(r, i);
         const u32 k = (u32)(bk & 1);
         const u64 b = bk >> 1;
         const u64 q = pp[i].pc.q;
@@ -1159,11 +1198,12 @@ __global__ void ks_finish_raised_kernel(const u64* __restrict__ ct, const u32 co
                                         u64* __restrict__ out, const u32 l, const u32 logN,
                                         const PrimeParams* __restrict__ pp, const RaiseArgs ra, const u64 total) {
     const u32 N = 1u << logN;
+    const SmallDiv dl(l);
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
         const u32 n = (u32)(idx & (N - 1));
         const u64 r = idx >> logN;  // (b, k, i) with i < l
-        const u32 i = (u32)(r % l);
-        const u64 bk = r / l;
+        u32 i;
+        const u64 bk = dl.divmod(r, i);
         const u32 k = (u32)(bk & 1);
         const u64 b = bk >> 1;
         const PrimeConst pc = pp[i].pc;
