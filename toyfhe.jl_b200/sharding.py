@@ -170,13 +170,31 @@ def keyswitch_residue_sharded(shard_op: Callable[[int, int], torch.Tensor], L: i
 
 def open_peer_exchange(ctx, L: int, max_batch: int, group=None):
     """One PeerExchange per rank for results of up to max_batch ciphertexts ([B][2][L][N]), the IPC handles swapped with
-    all_gather_object.  Collective: every rank of the group calls it."""
+    all_gather_object.  Collective: every rank of the group calls it.  Either every rank ends up with a fully attached
+    exchange or every rank raises (a rank whose allocation or IPC mapping fails does not leave the others waiting)."""
     from .engine import PeerExchange
     rank, world = _world(group)
-    x = PeerExchange(ctx, rank, world, max_batch * 2 * L * ctx.N)
+    x, err, handle = None, None, None
+    try:
+        x = PeerExchange(ctx, rank, world, max_batch * 2 * L * ctx.N)
+        handle = x.handle()
+    except Exception as e:                      # reported to the peers through the missing handle
+        err = e
     handles = [None] * world
-    dist.all_gather_object(handles, x.handle(), group=group)
-    x.attach(handles)
+    dist.all_gather_object(handles, handle, group=group)
+    ok = err is None and all(h is not None for h in handles)
+    if ok:
+        try:
+            x.attach(handles)
+        except Exception as e:                  # e.g. no peer access between two of the GPUs
+            err, ok = e, False
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{ctx.device}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        dist.barrier(group=group)               # nobody frees a buffer a peer may still be mapping
+        if x is not None:
+            x.close()
+        raise RuntimeError(f"peer exchange unavailable on at least one rank (this rank: {err!r})")
     dist.barrier(group=group)
     return x
 
